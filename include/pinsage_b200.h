@@ -1,0 +1,221 @@
+/*
+ * pinsage_b200.h -- C ABI of libpinsage_b200.so: the B200 (sm_100a) replacement for the
+ * PinSage inference + retrieval hot path of anisanazim/Movie-Recommendation-Engine.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes; every data pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host; no torch types.
+ *   - returns 0 (PB200_OK) or a negative pb200_status; never throws; the message for the
+ *     last failure on the calling thread is pb200_last_error().
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises the device or allocates device memory: scratch comes from the caller
+ *     (`workspace`, sized by the matching *_workspace_bytes query).
+ *   - matrices are row-major and contiguous; ids are int32 on the device.
+ *
+ * The reference has no FFI: its "operator API" is the Python classes cited on each entry
+ * point below (file:line under the reference repo).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ */
+#ifndef PINSAGE_B200_H
+#define PINSAGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+
+typedef void* pb200_stream_t; /* cudaStream_t */
+
+typedef enum {
+    PB200_OK = 0,
+    PB200_ERR_INVALID_ARG = -1, /* bad size / null pointer / unsupported combination */
+    PB200_ERR_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+    PB200_ERR_WORKSPACE = -3,   /* caller-provided workspace too small */
+    PB200_ERR_UNSUPPORTED = -4  /* shape outside what the kernels implement */
+} pb200_status;
+
+int pb200_abi_version(void);
+const char* pb200_last_error(void);
+/* number of kernel launches issued by this library on the calling process so far
+ * (bench.py reports the delta over the timed region as "gpu_launches") */
+int64_t pb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * S0  RandomWalkSampler.__init__/_prepare_adjacency_list   (utils/random_walk.py:11-50)
+ * Stable (edge-order preserving) CSR of a directed edge list + row-local cumulative
+ * weights, replacing the Python adjacency list.
+ * ------------------------------------------------------------------------------------ */
+
+/* flags_out[0] = smallest s in [0,10] such that w*2^s is integral for every edge (11 if
+ * none: use the float64 prefix path); flags_out[1] = number of negative or NaN weights
+ * (saturating); flags_out must be zero-initialised by the caller. */
+int pb200_edge_weight_probe(const float* edge_weights, int64_t num_edges, int32_t* flags_out,
+                            pb200_stream_t stream);
+
+size_t pb200_csr_build_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+
+/* edge_index: int64 [2, E] (row 0 = src, row 1 = dst), edge_weights: float32 [E] or NULL
+ * (=1.0, random_walk.py:45-48).  quant_shift >= 0: cum is uint32 [E], row-local inclusive
+ * prefix of w * 2^quant_shift (exact integers); quant_shift < 0: cum is float64 [E],
+ * sequential row-local prefix.  Outputs: row_ptr int64 [N+1], col int32 [E], cum.
+ * status_out int32 [4] (zero-initialised by the caller): [0] #edges with an id outside
+ * [0,N), [1] #weights not representable, [2] #rows whose total overflows uint32,
+ * [3] #non-empty rows with zero total weight.  Requires E < 2^32. */
+int pb200_csr_build(const int64_t* edge_index, const float* edge_weights, int64_t num_edges,
+                    int64_t num_nodes, int quant_shift, int64_t* row_ptr, int32_t* col,
+                    void* cum, int32_t* status_out, void* workspace, size_t workspace_bytes,
+                    pb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * S1-S3  _single_walk / sample_neighbors / batch_sample_neighbors
+ *                                                       (utils/random_walk.py:52-142)
+ * One warp per start node: num_walks weighted walks of <= walk_length steps driven by
+ * Philox4x32-10 (key = seed, counter = (start, walk, step/2, epoch)), visit counting in a
+ * per-warp shared-memory hash table, warp-level top-T by (count desc, first visit asc),
+ * weights = count / sum(kept counts).
+ *   starts int32 [n]; out_ids int32 [n,T] (-1 padded); out_counts int32 [n,T];
+ *   out_weights float32 [n,T] (= (float)((double)count/total)); out_nvalid int32 [n];
+ *   trace_out (optional, may be NULL) int32 [n, W, L], -1 where a walk had stopped.
+ * cum_kind: 0 = uint32 quanta, 1 = float64.  Limits: W*L <= 65535, W*L <= ~13000 (smem).
+ * ------------------------------------------------------------------------------------ */
+int pb200_walk_topt(const int64_t* row_ptr, const int32_t* col, const void* cum, int cum_kind,
+                    int64_t num_nodes, const int32_t* starts, int64_t n, int num_walks,
+                    int walk_length, int num_neighbors, uint64_t seed, uint32_t epoch,
+                    int32_t* out_ids, int32_t* out_counts, float* out_weights,
+                    int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream);
+
+/* Counting stage alone, given traces (parity "given the same walk traces"):
+ * trace int32 [n, V] (V = W*L visits in walk-major order, -1 = none). */
+int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_start, int num_neighbors,
+                     int32_t* out_ids, int32_t* out_counts, float* out_weights,
+                     int32_t* out_nvalid, pb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * P1-P4  neighbourhood pooling on padded ragged lists
+ *   ids int32 [n,T] (left-aligned lists, entries >= len ignored), weights float32 [n,T] or
+ *   NULL, list_len int32 [n] (#ids per row), weight_len int32 [n] or NULL (= list_len).
+ * ------------------------------------------------------------------------------------ */
+typedef enum {
+    /* model/pinsage.py:101-150 ImportancePooling: drop ids > M-1 WITH their weights,
+     * missing weight = 1, fp32 renormalise iff sum > 0 */
+    PB200_POOL_PINSAGE = 0,
+    /* model/layers.py:87-133 ImportancePoolingLayer (and WeightedMeanPoolingLayer with
+     * weights): drop ids >= M, use the FIRST len(valid) weights, zero sum -> uniform */
+    PB200_POOL_LAYERS = 1,
+    /* model/aggregators.py:49-91 WeightedAggregator: no id filtering (ids must be in
+     * range), weights[:len], zero sum -> mean */
+    PB200_POOL_AGGREGATOR = 2,
+    /* mean over ids < M (layers.py:189-191) */
+    PB200_POOL_MEAN = 3,
+    /* max over ids < M (layers.py:205-236 MaxPoolingLayer) */
+    PB200_POOL_MAX = 4
+} pb200_pool_mode;
+
+int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
+               const float* weights, const int32_t* list_len, const int32_t* weight_len,
+               int64_t n, int max_neighbors, int mode, float* out, pb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * G1-G3  fused [gather -> importance sum -> concat -> dense -> epilogue]
+ *   out[m,:] = epi( [A1[m,:K1] | A2row(m)] . W^T + bias )          out: float32 [n, N]
+ *   A1 float32 [n,K1]; W float32 [N, K1+K2] in nn.Linear layout; bias float32 [N] or NULL.
+ *   A2row(m) is  (a) absent (K2 = 0),  (b) dense A2[m,:K2]  (pool_x == NULL), or
+ *                (c) pooled on the fly from pool_x [pool_rows, K2] with the list arguments
+ *                    of pb200_pool (model/pinsage.py:232-240).
+ *   flags: PB200_EPI_RELU, PB200_EPI_L2NORM (F.normalize eps 1e-12), PB200_EPI_LAYERNORM
+ *   (gamma/beta = ln_gamma/ln_beta, eps 1e-5; aggregators.py:276-283).
+ *   precision: PB200_PREC_FP32 (CUDA-core FMA) or PB200_PREC_TF32 (tcgen05 kind::tf32).
+ * ------------------------------------------------------------------------------------ */
+#define PB200_EPI_RELU 1
+#define PB200_EPI_L2NORM 2
+#define PB200_EPI_LAYERNORM 4
+#define PB200_PREC_FP32 0
+#define PB200_PREC_TF32 1
+
+int pb200_gather_dense(const float* a1, int k1, const float* a2, int k2, const float* pool_x,
+                       int64_t pool_rows, const int32_t* ids, const float* weights,
+                       const int32_t* list_len, const int32_t* weight_len, int max_neighbors,
+                       int pool_mode, const float* w, const float* bias, const float* ln_gamma,
+                       const float* ln_beta, int64_t n, int n_out, int flags, int precision,
+                       float* out, pb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * E1/E2  exact search: GEMM fused with a streaming per-query top-k
+ *   E1 (utils/evaluation.py:119-130): inner product, descending, exclude_ids[q] removed
+ *   E2 (utils/nearest_neighbors.py:174-181, faiss IndexFlatL2): squared L2 via
+ *      |q|^2+|x|^2-2<q,x> clipped at 0, ascending.
+ *   queries float32 [nq,d], items float32 [nx,d]; exclude_ids int32 [nq] or NULL (-1 = none);
+ *   id_offset is added to every returned id (item-sharded search);
+ *   out_scores float32 [nq,k], out_ids int32 [nq,k] (-1 / +-inf padded when nx < k).
+ *   Ties are broken by ascending id, so results do not depend on tiling or sharding.
+ * ------------------------------------------------------------------------------------ */
+#define PB200_METRIC_IP 0
+#define PB200_METRIC_L2 1
+
+size_t pb200_topk_workspace_bytes(int64_t nq, int64_t nx, int dim, int k);
+int pb200_topk(const float* queries, int64_t nq, const float* items, int64_t nx, int dim, int k,
+               int metric, const int32_t* exclude_ids, int32_t id_offset, float* out_scores,
+               int32_t* out_ids, void* workspace, size_t workspace_bytes, pb200_stream_t stream);
+
+/* Merge of per-shard candidate lists (multi-GPU: after the NCCL all-gather).
+ * scores float32 [nq,c], ids int32 [nq,c] (id < 0 = padding); largest != 0 for IP. */
+int pb200_topk_merge(const float* scores, const int32_t* ids, int64_t nq, int c, int k,
+                     int largest, float* out_scores, int32_t* out_ids, pb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * L1-L3  LSHIndex (utils/nearest_neighbors.py:7-68; faiss.IndexLSH(d, nbits, rotate=True))
+ * ------------------------------------------------------------------------------------ */
+/* codes[v] = sign bits of (proj . x_v), packed LSB first; proj float32 [nbits, d];
+ * nbits % 32 == 0; codes uint8 [n, nbits/8]; proj_out (optional) float32 [n, nbits]. */
+int pb200_lsh_encode(const float* x, int64_t n, int dim, const float* proj, int nbits,
+                     uint8_t* codes, float* proj_out, pb200_stream_t stream);
+
+/* exhaustive Hamming top-k over all stored codes (what the reference computes).
+ * out_dist float32 [nq,k] (Hamming counts as floats, like faiss), out_ids int32 [nq,k]. */
+int pb200_hamming_topk(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x, int64_t nx,
+                       int code_bytes, int k, int32_t id_offset, float* out_dist,
+                       int32_t* out_ids, pb200_stream_t stream);
+
+/* bucketed mode: num_tables keys of (8*code_bytes/num_tables) in {8,16} bits.
+ * bucket_offsets int32 [num_tables, 2^key_bits + 1], bucket_ids int32 [num_tables, nx]. */
+size_t pb200_lsh_tables_workspace_bytes(int64_t nx, int code_bytes, int num_tables);
+int pb200_lsh_build_tables(const uint8_t* codes_x, int64_t nx, int code_bytes, int num_tables,
+                           int32_t* bucket_offsets, int32_t* bucket_ids, void* workspace,
+                           size_t workspace_bytes, pb200_stream_t stream);
+/* probe the query's bucket in every table, exact dedup (first matching table wins),
+ * re-rank by full-code Hamming (vectors == NULL) or inner product, warp top-k.
+ * out_ncand (optional) int32 [nq]: unique candidates examined per query. */
+int pb200_lsh_search_tables(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x,
+                            int64_t nx, int code_bytes, int num_tables,
+                            const int32_t* bucket_offsets, const int32_t* bucket_ids,
+                            const float* queries, const float* vectors, int dim, int k,
+                            float* out_scores, int32_t* out_ids, int32_t* out_ncand,
+                            pb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * I1/I2  WeakANDIndex (utils/nearest_neighbors.py:70-139; faiss.IndexIVFFlat, L2)
+ * ------------------------------------------------------------------------------------ */
+/* inverted lists from assignments: list_offsets int32 [nlist+1], list_ids int32 [n]
+ * (ascending id inside a list, like faiss appends), list_vecs float32 [n,d] = x[list_ids]. */
+size_t pb200_ivf_build_workspace_bytes(int64_t n, int nlist);
+int pb200_ivf_build(const float* x, int64_t n, int dim, const int32_t* assign, int nlist,
+                    int32_t* list_offsets, int32_t* list_ids, float* list_vecs, void* workspace,
+                    size_t workspace_bytes, pb200_stream_t stream);
+/* centroid update of one Lloyd iteration: centroids[c] = mean(list c) (unchanged if empty) */
+int pb200_ivf_centroid_update(const float* list_vecs, const int32_t* list_offsets, int nlist,
+                              int dim, float* centroids, pb200_stream_t stream);
+/* probes int32 [nq, nprobe] = nearest centroids (from pb200_topk on the centroids); scans
+ * those lists, k smallest squared L2 (direct difference form), -1 / +inf padded. */
+int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* probes,
+                     int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
+                     const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
+                     pb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINSAGE_B200_H */

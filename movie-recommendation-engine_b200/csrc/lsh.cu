@@ -1,0 +1,379 @@
+// lsh.cu -- K3: sign-random-projection LSH.
+//
+// Replaces LSHIndex.build/search (reference utils/nearest_neighbors.py:28-68), i.e.
+// faiss.IndexLSH(d, nbits, rotate_data=True): codes = sign bits of a fixed linear map, packed
+// LSB first; search = exhaustive Hamming top-k over all codes (what the reference really
+// computes: its third constructor argument is `rotate_data`, not a table count).
+// Also provides the bucketed mode the north star asks for (num_tables keys, bucket probe,
+// exact dedup, popcount or dot-product re-rank, warp top-k).
+//
+//   lsh_encode_kernel      fp32 projection (exact enough for the 1e-6 parity bar; bf16/tf32
+//                          tensor-core products would flip bits at |y| ~ 1e-3) + __ballot_sync
+//                          packing: lane j of a warp owns bit j of a 32-bit code word.
+//   hamming_topk_kernel    codes staged in shared memory (stride padded to avoid bank
+//                          conflicts), xor + popc per word, streaming warp top-k.
+//   table build / probe    counting sort per table; a candidate is accepted only in the first
+//                          table whose key matches (computed from the xor already needed for
+//                          the Hamming distance), which dedups exactly with no extra memory.
+#include "common.cuh"
+
+namespace pb200 {
+
+// ---------------------------------------------------------------- encode
+// block = 256 threads = 256 bits per pass; projection matrix chunk lives in shared memory
+// transposed ([d][256]) so that thread j reads column j conflict-free.
+__global__ void __launch_bounds__(256) lsh_encode_kernel(const float* __restrict__ x, int64_t n,
+                                                         int d, const float* __restrict__ proj,
+                                                         int nbits, int bit0, uint8_t* codes,
+                                                         float* proj_out) {
+    extern __shared__ float sm[];
+    float* a_t = sm;                 // [d][256]
+    float* xs = a_t + (size_t)d * 256;  // [d]
+    const int tid = threadIdx.x;
+    const int nb = min(256, nbits - bit0);  // bits handled by this launch (multiple of 32)
+    for (int idx = tid; idx < d * 256; idx += 256) {
+        const int j = idx / d, k = idx % d;  // coalesced read of proj rows
+        a_t[k * 256 + j] = j < nb ? proj[(int64_t)(bit0 + j) * d + k] : 0.f;
+    }
+    __syncthreads();
+    uint32_t* words = reinterpret_cast<uint32_t*>(codes);
+    const int words_per_code = nbits / 32;
+    for (int64_t v = blockIdx.x; v < n; v += gridDim.x) {
+        for (int k = tid; k < d; k += 256) xs[k] = x[v * d + k];
+        __syncthreads();
+        float y = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < d; ++k) y = fmaf(a_t[k * 256 + tid], xs[k], y);
+        const unsigned bits = __ballot_sync(kFull, y >= 0.f);  // lane j -> bit j: LSB first
+        if (tid < nb) {
+            if ((tid & 31) == 0) words[v * words_per_code + (bit0 + tid) / 32] = bits;
+            if (proj_out) proj_out[v * nbits + bit0 + tid] = y;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- exhaustive Hamming top-k
+constexpr int HQ = 64;    // queries per block (8 per warp)
+constexpr int HX = 256;   // items per shared-memory tile
+
+struct HammingParams {
+    const uint32_t* __restrict__ cq; int64_t nq;
+    const uint32_t* __restrict__ cx; int64_t nx;
+    int words, k_pass, k_total, col_off, id_offset;
+    float* __restrict__ out_dist; int32_t* __restrict__ out_ids;
+};
+
+__global__ void __launch_bounds__(256) hamming_topk_kernel(const HammingParams p) {
+    extern __shared__ uint32_t hs[];
+    const int W = p.words, WS = W + 1;          // padded stride: conflict-free lane-per-item reads
+    uint32_t* xs = hs;                           // [HX][WS]
+    uint32_t* qs = xs + HX * WS;                 // [HQ][W]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * HQ;
+    for (int idx = tid; idx < HQ * W; idx += 256) {
+        const int64_t qi = q0 + idx / W;
+        qs[idx] = qi < p.nq ? p.cq[qi * W + idx % W] : 0u;
+    }
+    TopkLane best[8]; float fb[8]; int fi[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        best[r].bad = INFINITY; best[r].id = INT_MAX; fb[r] = -INFINITY; fi[r] = -1;
+        const int64_t qi = q0 + warp * 8 + r;
+        if (qi < p.nq && p.col_off > 0) {
+            fb[r] = p.out_dist[qi * p.k_total + p.col_off - 1];
+            fi[r] = p.out_ids[qi * p.k_total + p.col_off - 1];
+            if (fi[r] < 0) { fb[r] = INFINITY; fi[r] = INT_MAX; }
+        }
+    }
+    for (int64_t x0 = 0; x0 < p.nx; x0 += HX) {
+        __syncthreads();
+        for (int idx = tid; idx < HX * W; idx += 256) {     // coalesced tile load
+            const int64_t xi = x0 + idx / W;
+            xs[(idx / W) * WS + idx % W] = xi < p.nx ? p.cx[xi * W + idx % W] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int64_t qi = q0 + warp * 8 + r;
+            if (qi >= p.nq) break;
+            const uint32_t* qc = qs + (warp * 8 + r) * W;
+            for (int it = lane; it < HX; it += 32) {
+                int dist = 0;
+                for (int w = 0; w < W; ++w) dist += __popc(xs[it * WS + w] ^ qc[w]);
+                const int64_t xi = x0 + it;
+                const int gid = (int)xi + p.id_offset;
+                const float bad = (float)dist;
+                const bool valid = xi < p.nx && better(fb[r], fi[r], bad, gid);
+                topk_offer(best[r], bad, gid, valid, p.k_pass, lane);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int64_t qi = q0 + warp * 8 + r;
+        if (qi >= p.nq) break;
+        if (lane < p.k_pass) {
+            const int64_t o = qi * p.k_total + p.col_off + lane;
+            const bool has = best[r].id != INT_MAX;
+            p.out_ids[o] = has ? best[r].id : -1;
+            p.out_dist[o] = has ? best[r].bad : INFINITY;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- bucketed tables
+__device__ __forceinline__ uint32_t code_key(const uint8_t* code, int t, int key_bytes) {
+    return key_bytes == 2 ? (uint32_t)code[2 * t] | ((uint32_t)code[2 * t + 1] << 8)
+                          : (uint32_t)code[t];
+}
+
+__global__ void table_hist_kernel(const uint8_t* __restrict__ codes, int64_t nx, int code_bytes,
+                                  int nt, int key_bytes, int32_t* offsets) {
+    const int nb = 1 << (8 * key_bytes);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx * nt;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = i / nt; const int t = (int)(i % nt);
+        atomicAdd(&offsets[(int64_t)t * (nb + 1) + 1 + code_key(codes + v * code_bytes, t, key_bytes)], 1);
+    }
+}
+
+// one block per table: in-place inclusive scan of counts[1..nb] -> offsets, cursor copy
+__global__ void __launch_bounds__(1024) table_scan_kernel(int32_t* offsets, int32_t* cursor, int nb) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry;
+    int32_t* off = offsets + (int64_t)blockIdx.x * (nb + 1);
+    int32_t* cur = cursor + (int64_t)blockIdx.x * nb;
+    if (threadIdx.x == 0) { carry = 0; off[0] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        int v = i < nb ? off[1 + i] : 0;
+        int s = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_tot[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFull, t, o); if (lane >= o) t += u; }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const int incl = s + (warp ? warp_tot[warp - 1] : 0) + carry;
+        if (i < nb) { off[1 + i] = incl; cur[i] = incl - v; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void table_fill_kernel(const uint8_t* __restrict__ codes, int64_t nx, int code_bytes,
+                                  int nt, int key_bytes, int32_t* cursor, int32_t* bucket_ids) {
+    const int nb = 1 << (8 * key_bytes);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx * nt;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = i / nt; const int t = (int)(i % nt);
+        const int pos = atomicAdd(&cursor[(int64_t)t * nb + code_key(codes + v * code_bytes, t, key_bytes)], 1);
+        bucket_ids[(int64_t)t * nx + pos] = (int32_t)v;
+    }
+}
+
+struct ProbeParams {
+    const uint8_t* __restrict__ cq; int64_t nq;
+    const uint8_t* __restrict__ cx; int64_t nx;
+    int code_bytes, nt, key_bytes;
+    const int32_t* __restrict__ offsets; const int32_t* __restrict__ bucket_ids;
+    const float* __restrict__ queries; const float* __restrict__ vectors; int d;
+    int k;
+    float* __restrict__ out_scores; int32_t* __restrict__ out_ids; int32_t* __restrict__ out_ncand;
+};
+
+// one warp per query; lane-per-candidate: one 32 B code (= one DRAM sector) per candidate
+__global__ void __launch_bounds__(256) lsh_probe_kernel(const ProbeParams p) {
+    extern __shared__ uint32_t ps[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = p.code_bytes / 4;
+    uint32_t* qc = ps + warp * W;
+    const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (qi >= p.nq) return;
+    for (int w = lane; w < W; w += 32) qc[w] = reinterpret_cast<const uint32_t*>(p.cq)[qi * W + w];
+    __syncwarp();
+    const int nb = 1 << (8 * p.key_bytes);
+    const bool dot = p.vectors != nullptr;
+    TopkLane e; e.bad = INFINITY; e.id = INT_MAX;
+    int ncand = 0;
+    for (int t = 0; t < p.nt; ++t) {
+        const uint32_t key = code_key(reinterpret_cast<const uint8_t*>(qc), t, p.key_bytes);
+        const int b0 = p.offsets[(int64_t)t * (nb + 1) + key];
+        const int b1 = p.offsets[(int64_t)t * (nb + 1) + key + 1];
+        for (int base = b0; base < b1; base += 32) {
+            const int j = base + lane;
+            bool valid = j < b1;
+            int id = -1; float bad = INFINITY;
+            if (valid) {
+                id = p.bucket_ids[(int64_t)t * p.nx + j];
+                const uint32_t* xc = reinterpret_cast<const uint32_t*>(p.cx) + (int64_t)id * W;
+                int dist = 0, first_match = p.nt;
+                for (int w = 0; w < W; ++w) {
+                    const uint32_t xr = __ldg(xc + w) ^ qc[w];
+                    dist += __popc(xr);
+                    // tables whose key lies in this word (keys are 1 or 2 bytes, word-aligned)
+                    const int per_word = 4 / p.key_bytes;
+                    for (int s = 0; s < per_word; ++s) {
+                        const uint32_t m = p.key_bytes == 2 ? 0xFFFFu << (16 * s) : 0xFFu << (8 * s);
+                        const int tt = w * per_word + s;
+                        if (tt < p.nt && (xr & m) == 0u && tt < first_match) first_match = tt;
+                    }
+                }
+                valid = first_match == t;      // dedup: only the first matching table reports it
+                bad = (float)dist;
+                if (valid && dot) {
+                    const float* xv = p.vectors + (int64_t)id * p.d;
+                    const float* qv = p.queries + qi * p.d;
+                    float s = 0.f;
+                    for (int c = 0; c < p.d; ++c) s = fmaf(__ldg(qv + c), __ldg(xv + c), s);
+                    bad = -s;
+                }
+            }
+            ncand += __popc(__ballot_sync(kFull, valid));
+            topk_offer(e, bad, id, valid, p.k, lane);
+        }
+    }
+    if (lane < p.k) {
+        const bool has = e.id != INT_MAX;
+        p.out_ids[qi * p.k + lane] = has ? e.id : -1;
+        p.out_scores[qi * p.k + lane] = has ? (dot ? -e.bad : e.bad) : (dot ? -INFINITY : INFINITY);
+    }
+    if (p.out_ncand && lane == 0) p.out_ncand[qi] = ncand;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_lsh_encode(const float* x, int64_t n, int dim, const float* proj, int nbits,
+                                uint8_t* codes, float* proj_out, pb200_stream_t stream) {
+    PB_REQUIRE(n >= 0 && dim > 0 && nbits > 0 && nbits % 32 == 0,
+               "lsh_encode: nbits must be a positive multiple of 32");
+    if (n == 0) return PB200_OK;
+    PB_REQUIRE(x && proj && codes, "lsh_encode: null pointer");
+    const size_t smem = ((size_t)dim * 256 + dim) * sizeof(float);
+    if (smem > 220 * 1024) {
+        set_error("lsh_encode: dim=%d needs %zu B shared memory (max dim 214)", dim, smem);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    PB_CUDA(cudaFuncSetAttribute(lsh_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    const int64_t blocks = n < kSMs ? n : kSMs;   // persistent: the matrix chunk is loaded once
+    for (int bit0 = 0; bit0 < nbits; bit0 += 256) {
+        lsh_encode_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
+            x, n, dim, proj, nbits, bit0, codes, proj_out);
+        int rc = check_launch("lsh_encode_kernel");
+        if (rc) return rc;
+    }
+    return PB200_OK;
+}
+
+extern "C" int pb200_hamming_topk(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x,
+                                  int64_t nx, int code_bytes, int k, int32_t id_offset,
+                                  float* out_dist, int32_t* out_ids, pb200_stream_t stream) {
+    PB_REQUIRE(nq >= 0 && nx >= 0 && code_bytes > 0 && code_bytes % 4 == 0 && code_bytes <= 256,
+               "hamming_topk: code_bytes must be a multiple of 4, <= 256");
+    PB_REQUIRE(k > 0 && k <= 1024, "hamming_topk: k must be in [1, 1024]");
+    if (nq == 0) return PB200_OK;
+    PB_REQUIRE(codes_q && out_dist && out_ids && (codes_x || nx == 0), "hamming_topk: null pointer");
+    const int W = code_bytes / 4;
+    const size_t smem = ((size_t)HX * (W + 1) + (size_t)HQ * W) * 4;
+    if (smem > 48 * 1024)
+        PB_CUDA(cudaFuncSetAttribute(hamming_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    for (int col = 0; col < k; col += 32) {
+        HammingParams p{};
+        p.cq = reinterpret_cast<const uint32_t*>(codes_q); p.nq = nq;
+        p.cx = reinterpret_cast<const uint32_t*>(codes_x); p.nx = nx;
+        p.words = W; p.k_pass = k - col < 32 ? k - col : 32; p.k_total = k; p.col_off = col;
+        p.id_offset = id_offset; p.out_dist = out_dist; p.out_ids = out_ids;
+        hamming_topk_kernel<<<(unsigned)ceil_div(nq, HQ), 256, smem, (cudaStream_t)stream>>>(p);
+        int rc = check_launch("hamming_topk_kernel");
+        if (rc) return rc;
+    }
+    return PB200_OK;
+}
+
+static int table_key_bytes(int code_bytes, int num_tables) {
+    if (num_tables <= 0 || code_bytes % num_tables) return 0;
+    const int kb = code_bytes / num_tables;
+    return (kb == 1 || kb == 2) ? kb : 0;
+}
+
+extern "C" size_t pb200_lsh_tables_workspace_bytes(int64_t nx, int code_bytes, int num_tables) {
+    (void)nx;
+    const int kb = table_key_bytes(code_bytes, num_tables);
+    if (!kb) return 0;
+    return (size_t)num_tables * ((size_t)1 << (8 * kb)) * sizeof(int32_t);
+}
+
+extern "C" int pb200_lsh_build_tables(const uint8_t* codes_x, int64_t nx, int code_bytes,
+                                      int num_tables, int32_t* bucket_offsets, int32_t* bucket_ids,
+                                      void* workspace, size_t workspace_bytes,
+                                      pb200_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int kb = table_key_bytes(code_bytes, num_tables);
+    if (!kb) {
+        set_error("lsh_build_tables: key width %d bits unsupported (need 8 or 16 bits per table)",
+                  num_tables > 0 ? 8 * code_bytes / num_tables : 0);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    PB_REQUIRE(nx >= 0 && bucket_offsets && workspace && (bucket_ids || nx == 0) &&
+               (codes_x || nx == 0), "lsh_build_tables: null pointer");
+    const int nb = 1 << (8 * kb);
+    if (workspace_bytes < pb200_lsh_tables_workspace_bytes(nx, code_bytes, num_tables)) {
+        set_error("lsh_build_tables: workspace too small");
+        return PB200_ERR_WORKSPACE;
+    }
+    int32_t* cursor = static_cast<int32_t*>(workspace);
+    PB_CUDA(cudaMemsetAsync(bucket_offsets, 0, (size_t)num_tables * (nb + 1) * sizeof(int32_t), stream));
+    const int64_t work = nx * num_tables;
+    const unsigned blocks = (unsigned)(work > 0 ? (ceil_div(work, 256) < kSMs * 8 ? ceil_div(work, 256) : kSMs * 8) : 1);
+    if (nx > 0) {
+        table_hist_kernel<<<blocks, 256, 0, stream>>>(codes_x, nx, code_bytes, num_tables, kb, bucket_offsets);
+        int rc = check_launch("table_hist_kernel");
+        if (rc) return rc;
+    }
+    table_scan_kernel<<<num_tables, 1024, 0, stream>>>(bucket_offsets, cursor, nb);
+    int rc = check_launch("table_scan_kernel");
+    if (rc) return rc;
+    if (nx > 0) {
+        table_fill_kernel<<<blocks, 256, 0, stream>>>(codes_x, nx, code_bytes, num_tables, kb, cursor, bucket_ids);
+        rc = check_launch("table_fill_kernel");
+    }
+    return rc;
+}
+
+extern "C" int pb200_lsh_search_tables(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x,
+                                       int64_t nx, int code_bytes, int num_tables,
+                                       const int32_t* bucket_offsets, const int32_t* bucket_ids,
+                                       const float* queries, const float* vectors, int dim, int k,
+                                       float* out_scores, int32_t* out_ids, int32_t* out_ncand,
+                                       pb200_stream_t stream) {
+    const int kb = table_key_bytes(code_bytes, num_tables);
+    if (!kb || code_bytes % 4) {
+        set_error("lsh_search_tables: unsupported code/table geometry");
+        return PB200_ERR_UNSUPPORTED;
+    }
+    PB_REQUIRE(k > 0 && k <= 32, "lsh_search_tables: k must be in [1, 32]");
+    PB_REQUIRE((vectors == nullptr) == (queries == nullptr) && (!vectors || dim > 0),
+               "lsh_search_tables: dot re-rank needs both queries and vectors");
+    if (nq == 0) return PB200_OK;
+    PB_REQUIRE(codes_q && codes_x && bucket_offsets && bucket_ids && out_scores && out_ids,
+               "lsh_search_tables: null pointer");
+    ProbeParams p{};
+    p.cq = codes_q; p.nq = nq; p.cx = codes_x; p.nx = nx; p.code_bytes = code_bytes;
+    p.nt = num_tables; p.key_bytes = kb; p.offsets = bucket_offsets; p.bucket_ids = bucket_ids;
+    p.queries = queries; p.vectors = vectors; p.d = dim; p.k = k;
+    p.out_scores = out_scores; p.out_ids = out_ids; p.out_ncand = out_ncand;
+    const size_t smem = (size_t)8 * (code_bytes / 4) * 4;
+    lsh_probe_kernel<<<(unsigned)ceil_div(nq, 8), 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("lsh_probe_kernel");
+}

@@ -1,0 +1,83 @@
+// pool.cu -- P1-P4: neighbourhood pooling as a stand-alone operator.
+//
+// Replaces the per-node Python loops of ImportancePooling (reference model/pinsage.py:101-150),
+// ImportancePoolingLayer / WeightedMeanPoolingLayer / MaxPoolingLayer (model/layers.py:87-236)
+// and WeightedAggregator / MeanAggregator (model/aggregators.py:13-91).
+// One warp per output row; neighbour rows are read as coalesced 16-byte vectors
+// (a 256-float row = two 512 B warp requests).  HBM/L2-bandwidth bound:
+// 4*dim*(valid+1) + 8*T bytes per row.
+#include "pool.cuh"
+
+namespace pb200 {
+
+template <bool kVec>
+__global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int dim,
+                                                   ListArgs a, int64_t n, float* __restrict__ out) {
+    extern __shared__ int32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    int* s_id = smem + (size_t)warp * 2 * a.T;
+    float* s_w = reinterpret_cast<float*>(s_id + a.T);
+    const bool is_max = a.mode == PB200_POOL_MAX;
+    for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < n; row += (int64_t)gridDim.x * wpb) {
+        const int nv = prepare_list(a, row, s_id, s_w, lane);
+        float* o = out + row * dim;
+        if (kVec) {
+            for (int c = lane * 4; c < dim; c += 128) {
+                float4 acc = is_max && nv ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int r = 0; r < nv; ++r) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)s_id[r] * dim + c));
+                    if (is_max) {
+                        acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
+                        acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+                    } else {
+                        const float w = s_w[r];
+                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    }
+                }
+                *reinterpret_cast<float4*>(o + c) = acc;
+            }
+        } else {
+            for (int c = lane; c < dim; c += 32) {
+                float acc = is_max && nv ? -INFINITY : 0.f;
+                for (int r = 0; r < nv; ++r) {
+                    const float v = __ldg(x + (int64_t)s_id[r] * dim + c);
+                    acc = is_max ? fmaxf(acc, v) : fmaf(s_w[r], v, acc);
+                }
+                o[c] = acc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
+                          const float* weights, const int32_t* list_len,
+                          const int32_t* weight_len, int64_t n, int max_neighbors, int mode,
+                          float* out, pb200_stream_t stream) {
+    PB_REQUIRE(n >= 0 && dim > 0 && max_neighbors > 0 && num_rows >= 0, "pool: bad sizes");
+    PB_REQUIRE(mode >= PB200_POOL_PINSAGE && mode <= PB200_POOL_MAX, "pool: unknown mode %d", mode);
+    if (n == 0) return PB200_OK;
+    PB_REQUIRE(x && ids && out, "pool: null pointer");
+    ListArgs a{ids, weights, list_len, weight_len, max_neighbors, mode, num_rows};
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * 2 * max_neighbors * sizeof(int32_t);
+    PB_REQUIRE(smem <= 200 * 1024, "pool: max_neighbors=%d too large", max_neighbors);
+    const bool vec = dim % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    auto kern = vec ? pool_kernel<true> : pool_kernel<false>;
+    if (smem > 48 * 1024)
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(n, wpb);
+    const int64_t cap = (int64_t)kSMs * 16;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(x, dim, a, n, out);
+    return check_launch("pool_kernel");
+}

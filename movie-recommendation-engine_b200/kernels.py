@@ -1,0 +1,273 @@
+"""Tensor-in / tensor-out wrappers over the C ABI (one function per entry point).
+
+These are the only callers of ``_native.lib()``.  They allocate outputs and workspaces with
+torch's caching allocator, pass raw pointers + the current stream, and never synchronise
+unless a host-side flag has to be read (build-time only).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _native as N
+from ._native import check, lib, ptr, stream_ptr
+
+
+@dataclass
+class CSR:
+    """Device-resident graph: stable CSR + row-local cumulative weights (S0)."""
+    row_ptr: torch.Tensor      # int64 [N+1]
+    col: torch.Tensor          # int32 [E]
+    cum: torch.Tensor          # uint32-as-int32 [E] (quanta) or float64 [E]
+    cum_kind: int              # 0 = uint32 quanta, 1 = float64
+    quant_shift: int           # weights were multiplied by 2**quant_shift (cum_kind 0)
+    num_nodes: int
+    num_edges: int
+
+    @property
+    def device(self):
+        return self.row_ptr.device
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.row_ptr, self.col, self.cum))
+
+
+def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_float=False):
+    dev = N.device_of(edge_index, edge_weights, device=device)
+    ei = N.dev_tensor(edge_index, torch.int64, dev)
+    if ei.dim() != 2 or ei.size(0) != 2:
+        raise ValueError("edge_index must have shape [2, num_edges]")
+    E = ei.size(1)
+    if num_nodes is None:                       # reference: edge_index.max() + 1
+        num_nodes = int(ei.max().item()) + 1 if E else 0
+    w = None if edge_weights is None else N.dev_tensor(edge_weights, torch.float32, dev)
+    if w is not None and w.numel() != E:
+        raise ValueError("edge_weights must have one entry per edge")
+    st = stream_ptr(dev)
+    quant_shift = 0
+    if w is not None and E:
+        flags = torch.zeros(2, dtype=torch.int32, device=dev)
+        check(lib().pb200_edge_weight_probe(ptr(w), E, ptr(flags), st), "edge_weight_probe")
+        shift, bad = flags.tolist()              # build-time sync
+        if bad:
+            raise ValueError(f"{bad} edge weights are negative, NaN or infinite")
+        quant_shift = -1 if (shift > 10 or force_float) else shift
+    row_ptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    cum = torch.empty(E, dtype=torch.int32 if quant_shift >= 0 else torch.float64, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    for attempt in range(2):
+        ws_bytes = lib().pb200_csr_build_workspace_bytes(E, num_nodes)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        check(lib().pb200_csr_build(ptr(ei), ptr(w), E, num_nodes, quant_shift, ptr(row_ptr),
+                                    ptr(col), ptr(cum) if E else None, ptr(status), ptr(ws),
+                                    ws_bytes, st), "csr_build")
+        bad_id, bad_w, overflow, zero_rows = status.tolist()
+        del ws
+        if bad_id:
+            raise IndexError(f"{bad_id} edges reference node ids outside [0, {num_nodes})")
+        if overflow and quant_shift >= 0 and attempt == 0:
+            # a row's total does not fit uint32 quanta: fall back to the float64 prefix path
+            quant_shift = -1
+            cum = torch.empty(E, dtype=torch.float64, device=dev)
+            status.zero_()
+            continue
+        if bad_w:
+            raise ValueError(f"{bad_w} edge weights not representable")
+        if zero_rows:
+            raise ValueError(f"{zero_rows} nodes have out-edges whose weights sum to zero "
+                             "(the reference's np.random.choice would raise on NaN probabilities)")
+        break
+    return CSR(row_ptr, col, cum, 0 if quant_shift >= 0 else 1, quant_shift, num_nodes, E)
+
+
+def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epoch=0,
+              return_trace=False):
+    dev = csr.device
+    s = N.dev_tensor(starts, torch.int32, dev)
+    n = s.numel()
+    T = int(num_neighbors)
+    ids = torch.empty((n, T), dtype=torch.int32, device=dev)
+    counts = torch.empty((n, T), dtype=torch.int32, device=dev)
+    weights = torch.empty((n, T), dtype=torch.float32, device=dev)
+    nvalid = torch.empty(n, dtype=torch.int32, device=dev)
+    trace = torch.empty((n, num_walks, walk_length), dtype=torch.int32, device=dev) \
+        if return_trace else None
+    check(lib().pb200_walk_topt(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cum) if csr.num_edges else
+                                ptr(csr.row_ptr), csr.cum_kind, csr.num_nodes, ptr(s), n,
+                                int(num_walks), int(walk_length), T, int(seed) & (2**64 - 1),
+                                int(epoch) & 0xFFFFFFFF, ptr(ids), ptr(counts), ptr(weights),
+                                ptr(nvalid), ptr(trace), stream_ptr(dev)), "walk_topt")
+    return (ids, counts, weights, nvalid, trace) if return_trace else (ids, counts, weights, nvalid)
+
+
+def count_topt(trace, num_neighbors):
+    dev = N.device_of(trace)
+    tr = N.dev_tensor(trace, torch.int32, dev)
+    n = tr.size(0)
+    V = tr.numel() // max(n, 1)
+    T = int(num_neighbors)
+    ids = torch.empty((n, T), dtype=torch.int32, device=dev)
+    counts = torch.empty((n, T), dtype=torch.int32, device=dev)
+    weights = torch.empty((n, T), dtype=torch.float32, device=dev)
+    nvalid = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib().pb200_count_topt(ptr(tr), n, V, T, ptr(ids), ptr(counts), ptr(weights),
+                                 ptr(nvalid), stream_ptr(dev)), "count_topt")
+    return ids, counts, weights, nvalid
+
+
+def pool(x, ids, weights, list_len, weight_len, mode):
+    dev = N.device_of(x)
+    x = N.dev_tensor(x, torch.float32, dev)
+    n, T = ids.shape
+    out = torch.empty((n, x.size(1)), dtype=torch.float32, device=dev)
+    check(lib().pb200_pool(ptr(x), x.size(0), x.size(1), ptr(ids), ptr(weights), ptr(list_len),
+                           ptr(weight_len), n, T, mode, ptr(out), stream_ptr(dev)), "pool")
+    return out
+
+
+def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N.POOL_PINSAGE,
+                 flags=0, precision=N.PREC_FP32, ln_gamma=None, ln_beta=None, n=None):
+    """out = epi([a1 | a2-or-pooled] @ w.T + bias).  lists = (ids, weights, list_len, weight_len)."""
+    dev = N.device_of(w)
+    k1 = 0 if a1 is None else a1.size(1)
+    if n is None:
+        n = a1.size(0) if a1 is not None else (a2.size(0) if a2 is not None else lists[0].size(0))
+    k2 = 0
+    if a2 is not None:
+        k2 = a2.size(1)
+    elif pool_x is not None:
+        k2 = pool_x.size(1)
+    n_out, K = w.shape
+    if K != k1 + k2:
+        raise ValueError(f"weight has {K} input columns, inputs provide {k1}+{k2}")
+    ids = wts = ll = wl = None
+    T = 0
+    if pool_x is not None:
+        ids, wts, ll, wl = lists
+        T = ids.size(1)
+    out = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    check(lib().pb200_gather_dense(ptr(a1), k1, ptr(a2), k2, ptr(pool_x),
+                                   0 if pool_x is None else pool_x.size(0), ptr(ids), ptr(wts),
+                                   ptr(ll), ptr(wl), T, pool_mode, ptr(w), ptr(bias),
+                                   ptr(ln_gamma), ptr(ln_beta), n, n_out, flags, precision,
+                                   ptr(out), stream_ptr(dev)), "gather_dense")
+    return out
+
+
+def topk(queries, items, k, metric, exclude_ids=None, id_offset=0):
+    dev = N.device_of(items, queries)
+    q = N.dev_tensor(queries, torch.float32, dev)
+    x = N.dev_tensor(items, torch.float32, dev)
+    if q.dim() == 1:
+        q = q[None]
+    nq, d = q.shape
+    nx = x.size(0)
+    if x.size(1) != d:
+        raise RuntimeError(f"dimension mismatch: queries {d}, items {x.size(1)}")
+    ex = None if exclude_ids is None else N.dev_tensor(exclude_ids, torch.int32, dev)
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    ws_bytes = lib().pb200_topk_workspace_bytes(nq, nx, d, k)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    check(lib().pb200_topk(ptr(q), nq, ptr(x), nx, d, k, metric, ptr(ex), int(id_offset),
+                           ptr(scores), ptr(ids), ptr(ws), ws_bytes, stream_ptr(dev)), "topk")
+    return scores, ids
+
+
+def topk_merge(scores, ids, k, largest):
+    dev = N.device_of(scores)
+    s = N.dev_tensor(scores, torch.float32, dev)
+    i = N.dev_tensor(ids, torch.int32, dev)
+    nq, c = s.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    check(lib().pb200_topk_merge(ptr(s), ptr(i), nq, c, k, 1 if largest else 0, ptr(out_s),
+                                 ptr(out_i), stream_ptr(dev)), "topk_merge")
+    return out_s, out_i
+
+
+def lsh_encode(x, proj, return_projection=False):
+    dev = N.device_of(x, proj)
+    x = N.dev_tensor(x, torch.float32, dev)
+    proj = N.dev_tensor(proj, torch.float32, dev)
+    n, d = x.shape
+    nbits = proj.size(0)
+    codes = torch.empty((n, nbits // 8), dtype=torch.uint8, device=dev)
+    y = torch.empty((n, nbits), dtype=torch.float32, device=dev) if return_projection else None
+    check(lib().pb200_lsh_encode(ptr(x), n, d, ptr(proj), nbits, ptr(codes), ptr(y),
+                                 stream_ptr(dev)), "lsh_encode")
+    return (codes, y) if return_projection else codes
+
+
+def hamming_topk(codes_q, codes_x, k, id_offset=0):
+    dev = N.device_of(codes_x)
+    nq, cb = codes_q.shape
+    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    check(lib().pb200_hamming_topk(ptr(codes_q), nq, ptr(codes_x), codes_x.size(0), cb, k,
+                                   int(id_offset), ptr(dist), ptr(ids), stream_ptr(dev)),
+          "hamming_topk")
+    return dist, ids
+
+
+def lsh_build_tables(codes_x, num_tables):
+    dev = N.device_of(codes_x)
+    nx, cb = codes_x.shape
+    key_bits = 8 * cb // num_tables
+    offsets = torch.empty((num_tables, (1 << key_bits) + 1), dtype=torch.int32, device=dev)
+    bucket_ids = torch.empty((num_tables, max(nx, 1)), dtype=torch.int32, device=dev)
+    ws_bytes = lib().pb200_lsh_tables_workspace_bytes(nx, cb, num_tables)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    check(lib().pb200_lsh_build_tables(ptr(codes_x), nx, cb, num_tables, ptr(offsets),
+                                       ptr(bucket_ids), ptr(ws), ws_bytes, stream_ptr(dev)),
+          "lsh_build_tables")
+    return offsets, bucket_ids
+
+
+def lsh_search_tables(codes_q, codes_x, num_tables, offsets, bucket_ids, k, queries=None,
+                      vectors=None):
+    dev = N.device_of(codes_x)
+    nq, cb = codes_q.shape
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    ncand = torch.empty(nq, dtype=torch.int32, device=dev)
+    d = 0 if vectors is None else vectors.size(1)
+    check(lib().pb200_lsh_search_tables(ptr(codes_q), nq, ptr(codes_x), codes_x.size(0), cb,
+                                        num_tables, ptr(offsets), ptr(bucket_ids), ptr(queries),
+                                        ptr(vectors), d, k, ptr(scores), ptr(ids), ptr(ncand),
+                                        stream_ptr(dev)), "lsh_search_tables")
+    return scores, ids, ncand
+
+
+def ivf_build(x, assign, nlist):
+    dev = N.device_of(x)
+    n, d = x.shape
+    offsets = torch.empty(nlist + 1, dtype=torch.int32, device=dev)
+    list_ids = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    list_vecs = torch.empty((max(n, 1), d), dtype=torch.float32, device=dev)
+    ws_bytes = lib().pb200_ivf_build_workspace_bytes(n, nlist)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    check(lib().pb200_ivf_build(ptr(x), n, d, ptr(assign), nlist, ptr(offsets), ptr(list_ids),
+                                ptr(list_vecs), ptr(ws), ws_bytes, stream_ptr(dev)), "ivf_build")
+    return offsets, list_ids[:n], list_vecs[:n]
+
+
+def ivf_centroid_update(list_vecs, offsets, centroids):
+    dev = N.device_of(centroids)
+    check(lib().pb200_ivf_centroid_update(ptr(list_vecs), ptr(offsets), centroids.size(0),
+                                          centroids.size(1), ptr(centroids), stream_ptr(dev)),
+          "ivf_centroid_update")
+    return centroids
+
+
+def ivf_search(queries, probes, offsets, list_ids, list_vecs, k):
+    dev = N.device_of(list_vecs)
+    nq, d = queries.shape
+    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    check(lib().pb200_ivf_search(ptr(queries), nq, d, ptr(probes), probes.size(1), ptr(offsets),
+                                 ptr(list_ids), ptr(list_vecs), k, ptr(dist), ptr(ids),
+                                 stream_ptr(dev)), "ivf_search")
+    return dist, ids

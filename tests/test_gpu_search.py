@@ -1,0 +1,177 @@
+"""GPU parity: E1/E2 exact search, L1-L3 LSH, I1/I2 IVF, top-k merge through the C ABI.
+E1 is pinned by the reference golden; E2/LSH/IVF are compared with the faiss restatements in
+the oracle (PARITY UNPINNED: faiss is absent offline), conditional on shared parameters."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import mre_b200  # noqa: F401
+    from mre_b200 import kernels
+    assert torch.cuda.is_available()
+    return kernels
+
+
+def _data(n, d, seed, normalise=True):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    if normalise:
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def test_exact_ip_vs_reference_golden(K):
+    from mre_b200.utils.evaluation import generate_recommendations, generate_recommendations_batch
+    g = Hh.load("exact.npz")
+    emb = torch.from_numpy(g["emb"]).cuda()
+    for q, want in zip(g["queries"], g["ids"]):
+        np.testing.assert_array_equal(generate_recommendations(emb, int(q), k=10), want)
+    np.testing.assert_array_equal(generate_recommendations_batch(emb, g["queries"], 10, False), g["ids_incl"])
+    got = generate_recommendations(torch.from_numpy(g["emb"]), 3, k=10)        # CPU tensor input
+    np.testing.assert_array_equal(got, g["ids"][1])
+    assert got.dtype == np.int64
+
+
+@pytest.mark.parametrize("nq,nx,d,k", [(1, 1, 1, 1), (5, 40, 7, 10), (70, 3000, 64, 10), (130, 1000, 128, 32),
+                                       (3, 200, 33, 50), (64, 65, 16, 11)])
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_exact_topk_vs_oracle(K, nq, nx, d, k, metric):
+    from mre_b200 import _native as N
+    x, q = _data(nx, d, 1), _data(nq, d, 2)
+    kk = min(k, nx)
+    s, i = K.topk(torch.from_numpy(q), torch.from_numpy(x), k, N.METRIC_IP if metric == "ip" else N.METRIC_L2)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    rs, ri = (O.exact_ip if metric == "ip" else O.exact_l2)(x, q, kk)
+    np.testing.assert_allclose(s[:, :kk], rs, atol=2e-5)                  # compare by score
+    assert (i[:, :kk] == ri).mean() > 0.98                                # ids, up to fp ties
+    if kk < k:                                                            # padding convention
+        assert (i[:, kk:] == -1).all()
+        assert np.all(np.isinf(s[:, kk:]))
+    # the returned ids really have the returned scores
+    full = q @ x.T if metric == "ip" else np.maximum((q * q).sum(1)[:, None] + (x * x).sum(1)[None] - 2 * q @ x.T, 0)
+    np.testing.assert_allclose(np.take_along_axis(full, i[:, :kk].astype(np.int64), 1), s[:, :kk], atol=2e-5)
+
+
+def test_topk_exclude_offset_and_merge(K):
+    """Item-sharded search + merge == unsharded search (the multi-GPU path on one GPU)."""
+    from mre_b200 import _native as N
+    x, q = _data(5000, 48, 3), _data(100, 48, 4)
+    xt, qt = torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda()
+    excl = torch.arange(100, dtype=torch.int32)
+    s_full, i_full = K.topk(qt, xt, 10, N.METRIC_IP, exclude_ids=excl)
+    parts = [K.topk(qt, xt[a:b].contiguous(), 10, N.METRIC_IP, exclude_ids=excl, id_offset=a)
+             for a, b in [(0, 1300), (1300, 2600), (2600, 3800), (3800, 5000)]]
+    s_m, i_m = K.topk_merge(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), 10, True)
+    np.testing.assert_array_equal(i_m.cpu().numpy(), i_full.cpu().numpy())      # bitwise: total order
+    np.testing.assert_array_equal(s_m.cpu().numpy(), s_full.cpu().numpy())
+    rs, ri = O.topk_merge([p[0].cpu().numpy() for p in parts], [p[1].cpu().numpy() for p in parts], 10, True)
+    np.testing.assert_array_equal(i_m.cpu().numpy(), ri)
+    assert not (i_full.cpu().numpy() == np.arange(100)[:, None]).any()          # self excluded
+
+
+def test_lsh_codes_and_exhaustive_search(K):
+    """L1/L2: codes bit-exact except projections within 1e-6 of zero; Hamming top-k exact."""
+    from mre_b200.utils.nearest_neighbors import LSHIndex
+    d, nbits, n = 128, 256, 3000
+    x = _data(n, d, 5)
+    A = O.lsh_rotation(d, nbits)
+    ref_codes, y = O.lsh_encode(x, A)
+    codes, y_gpu = K.lsh_encode(torch.from_numpy(x), torch.from_numpy(A), return_projection=True)
+    codes = codes.cpu().numpy()
+    diff_bits = np.unpackbits(codes ^ ref_codes, axis=1, bitorder="little").astype(bool)
+    assert np.all(np.abs(y[diff_bits]) < 1e-6)
+    np.testing.assert_allclose(y_gpu.cpu().numpy(), y, atol=1e-5)
+    idx = LSHIndex(d, nbits, 16, projection=A)
+    idx.build(x)
+    assert idx.index.ntotal == n
+    dist, ids = idx.search(x[:200], k=10)
+    assert dist.dtype == np.float32 and ids.dtype == np.int64 and dist.shape == (200, 10)
+    rd, ri = O.lsh_search_exhaustive(codes, codes[:200], 10)
+    np.testing.assert_array_equal(dist, rd)                                 # Hamming ints, exact
+    np.testing.assert_array_equal(ids, ri)                                  # (dist, id) total order
+    assert (ids[:, 0] == np.arange(200)).all() and (dist[:, 0] == 0).all()
+    d2, i2 = idx.search(x[:7], k=40)                                        # k > 32: multi-pass
+    rd2, ri2 = O.lsh_search_exhaustive(codes, codes[:7], 40)
+    np.testing.assert_array_equal(d2, rd2); np.testing.assert_array_equal(i2, ri2)
+
+
+@pytest.mark.parametrize("rerank", ["hamming", "dot"])
+def test_lsh_tables_mode(K, rerank):
+    """L3 (north-star bucketed mode): candidates = items sharing >= 1 of the 16 keys; exact dedup."""
+    from mre_b200.utils.nearest_neighbors import LSHIndex
+    import mre_b200.synthetic as S
+    d, nbits, n = 64, 256, 4000
+    x = S.spread_embeddings(n, d, seed=1, clusters=64, noise=0.05).numpy()
+    A = O.lsh_rotation(d, nbits)
+    idx = LSHIndex(d, nbits, 16, mode="tables", rerank=rerank, projection=A)
+    idx.build(x)
+    q = x[:300]
+    dist, ids = idx.search(q, k=10)
+    codes = idx.codes.cpu().numpy()
+    rd, ri, ncand = O.lsh_search_tables(codes, codes[:300], 10, 16,
+                                        vectors=x if rerank == "dot" else None, queries=q)
+    np.testing.assert_array_equal(idx.last_num_candidates.cpu().numpy(), ncand)   # dedup is exact
+    if rerank == "hamming":
+        np.testing.assert_array_equal(ids, ri)
+        np.testing.assert_array_equal(dist[ri >= 0], rd[ri >= 0])
+    else:
+        ok = ri >= 0
+        np.testing.assert_allclose(dist[ok], rd[ok], atol=2e-5)
+        assert (ids == ri).mean() > 0.98
+    assert ((ids == -1) == (ri == -1)).all()
+
+
+def test_ivf_weak_and(K):
+    """I1/I2 with shared centroids: assignments, list layout and search vs the restatement."""
+    from mre_b200.utils.nearest_neighbors import WeakANDIndex, train_kmeans
+    import mre_b200.synthetic as S
+    n, d, nlist = 6000, 32, 100
+    x = S.spread_embeddings(n, d, seed=2, clusters=80, noise=0.2).numpy()
+    cent = O.kmeans(x, nlist, niter=5)
+    idx = WeakANDIndex(d, nlist, 10, centroids=cent)
+    idx.build(x)
+    assert idx.index.ntotal == n and idx.quantizer.ntotal == nlist
+    a_ref = O.ivf_assign(x, cent)
+    a_gpu = idx.assign.cpu().numpy()
+    assert (a_gpu == a_ref).mean() > 0.999
+    offsets, list_ids, _ = idx._lists
+    offsets, list_ids = offsets.cpu().numpy(), list_ids.cpu().numpy()
+    for l in (0, 17, 99):                                   # ascending ids inside a list
+        seg = list_ids[offsets[l]:offsets[l + 1]]
+        np.testing.assert_array_equal(seg, np.nonzero(a_gpu == l)[0])
+    dist, ids = idx.search(x[:250], k=10)
+    assert idx.index.nprobe == 20
+    rd, ri = O.ivf_search(x, cent, a_gpu, x[:250], 10, 20)
+    np.testing.assert_allclose(dist, rd, atol=2e-5)
+    assert (ids == ri).mean() > 0.98
+    # tiny lists: fewer than k results -> -1 padding
+    few = WeakANDIndex(d, 4, centroids=x[:4] * 10.0 + np.eye(4, d, dtype=np.float32) * 100)
+    few.build(x[:6])
+    dd, ii = few.search(x[:2], k=10)
+    assert (ii[:, 6:] == -1).all() and np.isinf(dd[:, 6:]).all()
+    # GPU k-means: every Lloyd iteration does not increase the quantisation error
+    xt = torch.from_numpy(x).cuda()
+    c5 = train_kmeans(xt, 16, niter=5)
+    c1 = train_kmeans(xt, 16, niter=1)
+    err = lambda c: float(K.topk(xt, c, 1, 1)[0].sum())
+    assert err(c5) <= err(c1) * 1.0001
+
+
+def test_benchmark_search_methods_dict(K):
+    from mre_b200.utils.nearest_neighbors import benchmark_search_methods
+    import mre_b200.synthetic as S
+    x = S.spread_embeddings(3000, 64, seed=3, clusters=50, noise=0.2)
+    res = benchmark_search_methods(x, x[:100], k=10)
+    assert set(res) == {"exact", "lsh", "ivf"}
+    for m in res.values():
+        assert {"distances", "indices", "search_time", "index_size", "method"} <= set(m)
+        assert m["indices"].shape == (100, 10) and m["index_size"] == 3000
+    assert res["ivf"]["recall"] > 0.8 and 0.0 <= res["lsh"]["recall"] <= 1.0
+    assert (res["exact"]["indices"][:, 0] == np.arange(100)).all()

@@ -1,0 +1,125 @@
+"""GPU parity: S0-S3 (CSR build, walk, count, top-T) through the C ABI vs the oracle and the
+reference-generated golden fixtures.  Bit-exact bar (integer / index work)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import mre_b200  # noqa: F401
+    from mre_b200 import kernels
+    assert torch.cuda.is_available()
+    return kernels
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["walk_quant.npz", "walk_unit.npz", "walk_float.npz"])
+def test_csr_and_walk_match_reference_golden(K, name):
+    c = Hh.walk_case(name)
+    N = int(c["ei"].max()) + 1
+    csr = K.csr_build(torch.from_numpy(c["ei"]), None if c["w"] is None else torch.from_numpy(c["w"]),
+                      num_nodes=N)
+    qs = Hh.quant_shift_for(c["w"])
+    assert csr.quant_shift == qs and csr.cum_kind == (0 if qs >= 0 else 1)
+    row_ptr, col, cum = O.csr_build(c["ei"], c["w"], N, quant_shift=qs)
+    np.testing.assert_array_equal(_np(csr.row_ptr), row_ptr)
+    np.testing.assert_array_equal(_np(csr.col), col)
+    got_cum = _np(csr.cum).view(np.uint32) if qs >= 0 else _np(csr.cum)
+    np.testing.assert_array_equal(got_cum, cum)
+    ids, counts, w32, nvalid, trace = K.walk_topt(csr, torch.from_numpy(c["starts"]), c["W"], c["L"],
+                                                  c["T"], c["seed"], c["epoch"], return_trace=True)
+    # vs the UNMODIFIED reference driven by the same uniforms
+    np.testing.assert_array_equal(_np(nvalid), c["nvalid"])
+    np.testing.assert_array_equal(_np(ids).astype(np.int64), c["ids"])
+    np.testing.assert_array_equal(_np(w32), c["weights"].astype(np.float32))
+    # vs the C oracle: counts and full traces
+    o = O.c_walk_topt(row_ptr, col, cum, c["starts"], c["W"], c["L"], c["T"], c["seed"], c["epoch"],
+                      return_trace=True)
+    np.testing.assert_array_equal(_np(counts), o["counts"])
+    np.testing.assert_array_equal(_np(trace), o["trace"])
+    # counting stage alone, given the traces ("same walk traces" bar)
+    i2, c2, w2, n2 = K.count_topt(trace.reshape(trace.size(0), -1), c["T"])
+    np.testing.assert_array_equal(_np(i2), _np(ids)); np.testing.assert_array_equal(_np(c2), _np(counts))
+    np.testing.assert_array_equal(_np(w2), _np(w32)); np.testing.assert_array_equal(_np(n2), _np(nvalid))
+
+
+def test_walk_c1_full_vs_oracle(K):
+    """Config C1 (2k movies / 5k users / 100k ratings), all items, both layer samples."""
+    import mre_b200.synthetic as S
+    M, U, R = S.CONFIGS["C1"][:3]
+    ei, w = S.bipartite_graph(M, U, R, seed=0)
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=M + U)
+    row_ptr, col, cum = O.c_csr_build(ei, w, M + U, 1)
+    np.testing.assert_array_equal(_np(csr.row_ptr), row_ptr)
+    np.testing.assert_array_equal(_np(csr.cum).view(np.uint32), cum)
+    for epoch in range(2):
+        ids, counts, w32, nvalid = K.walk_topt(csr, torch.arange(M), 100, 2, 10, 1234, epoch)
+        o = O.c_walk_topt(row_ptr, col, cum, np.arange(M), 100, 2, 10, 1234, epoch)
+        np.testing.assert_array_equal(_np(ids), o["ids"])
+        np.testing.assert_array_equal(_np(counts), o["counts"])
+        np.testing.assert_array_equal(_np(w32), o["w32"])
+        np.testing.assert_array_equal(_np(nvalid), o["nvalid"])
+
+
+def test_walk_is_batching_and_order_invariant(K):
+    """Counter-based RNG: a start node's result does not depend on the batch it is in (this is
+    what makes 1/2/4/8-GPU sharding bitwise identical)."""
+    import mre_b200.synthetic as S
+    ei, w = S.bipartite_graph(500, 900, 12000, seed=2)
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=1400)
+    full = K.walk_topt(csr, torch.arange(500), 100, 2, 10, 5, 0)
+    perm = torch.randperm(500, generator=torch.Generator().manual_seed(0))
+    part = K.walk_topt(csr, perm[:123], 100, 2, 10, 5, 0)
+    for a, b in zip(full, part):
+        np.testing.assert_array_equal(_np(a)[perm[:123].numpy()], _np(b))
+    other = K.walk_topt(csr, torch.arange(500), 100, 2, 10, 5, 1)     # next epoch differs
+    assert not np.array_equal(_np(full[0]), _np(other[0]))
+
+
+@pytest.mark.parametrize("W,L,T", [(1, 1, 1), (7, 5, 3), (33, 2, 64), (100, 2, 50), (300, 4, 10)])
+def test_walk_shapes_vs_oracle(K, W, L, T):
+    c = Hh.walk_case("walk_quant.npz")
+    N = int(c["ei"].max()) + 1
+    csr = K.csr_build(torch.from_numpy(c["ei"]), torch.from_numpy(c["w"]), num_nodes=N)
+    row_ptr, col, cum = O.c_csr_build(c["ei"], c["w"], N, 1)
+    starts = np.arange(N)
+    ids, counts, w32, nvalid = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 42, 9)
+    o = O.c_walk_topt(row_ptr, col, cum, starts, W, L, T, 42, 9)
+    np.testing.assert_array_equal(_np(ids), o["ids"])
+    np.testing.assert_array_equal(_np(counts), o["counts"])
+    np.testing.assert_array_equal(_np(w32), o["w32"])
+    np.testing.assert_array_equal(_np(nvalid), o["nvalid"])
+
+
+def test_sampler_dropin_api(K):
+    from mre_b200.utils.random_walk import RandomWalkSampler
+    c = Hh.walk_case("walk_quant.npz")
+    s = RandomWalkSampler(torch.from_numpy(c["ei"]), torch.from_numpy(c["w"]), walk_length=2,
+                          num_walks=100, seed=c["seed"])
+    nbrs, wts = s.batch_sample_neighbors(c["starts"].tolist(), 10)      # epoch 0
+    for r in range(len(nbrs)):
+        nv = c["nvalid"][r]
+        assert nbrs[r] == c["ids"][r, :nv].tolist()
+        assert wts[r] == c["weights"][r, :nv].tolist()                   # float64, bit-exact
+    assert all(isinstance(v, int) for v in nbrs[0]) and all(isinstance(v, float) for v in wts[0])
+    n1, w1 = s.sample_neighbors(0, 10)                                    # epoch 1: new sample
+    assert len(n1) == len(w1) <= 10 and abs(sum(w1) - 1.0) < 1e-12
+    walk = s._single_walk(3)
+    assert walk[0] == 3 and 1 <= len(walk) <= 3
+    adj = s.adj_list
+    assert len(adj) == int(c["ei"].max()) + 1
+    e0 = [(int(d), float(w)) for sidx, d, w in zip(c["ei"][0], c["ei"][1], c["w"]) if sidx == 0]
+    assert adj[0] == e0                                                   # edge order preserved
+    with pytest.raises(IndexError):
+        s.sample_neighbors(10**6)
+    empty_n, empty_w = s.sample_neighbors(len(adj) - 1)                   # node without out-edges
+    assert empty_n == [] and empty_w == []
