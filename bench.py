@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- item embeddings/s of the full 2-layer PinSage get_embeddings hot path.
+
+Workload (BASELINE.json configs[1], "C2"): ML-25M-shaped synthetic graph (62,423 items,
+162,541 users, 25,000,095 ratings), F=128 -> H=256 -> E=128, 2 layers, W=100 walks of length 2,
+T=10 neighbours.  One step = 2 x [walk/count/top-T kernel over all items] + fused forward
+(input projection, 2 fused gather+dense conv layers, output projection + L2 norm).
+
+  value  items/s with the feature matrix already resident in HBM (CUDA events, per step)
+  e2e    items/s through the public API (PinSage.get_embeddings) with HOST buffers: pinned
+         features H2D and embeddings D2H inside the timed region, host wall clock
+  roofline   the walk kernel (dominant): algorithmic bytes (summed exactly
+             over the executed steps of one launch from its trace) / CUDA-event duration
+  cpu_baseline   the oracle port (C walk sampler on all host threads + numpy forward) on a
+                 bounded sample, rank 0 at N=1
+
+N > 1 (torchrun): rows are split across ranks (strong scaling over the fixed catalogue), one
+all-gather of h per layer over NCCL; time = max over ranks.
+`--impl reference` times the CPU port alone (rank 0) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "item embeddings/sec (2-layer PinSage)"
+UNIT = "items/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2"])
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="start items per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+        self.active = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                        if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_inputs(workload):
+    import mre_b200  # noqa: F401
+    from mre_b200 import synthetic as S
+    M, U, R, F_, Hd, E_, layers = S.CONFIGS[workload]
+    t0 = time.time()
+    ei, w = S.bipartite_graph(M, U, R, seed=0)
+    x = S.features(M, F_, seed=0)
+    return dict(M=M, U=U, R=R, F=F_, H=Hd, E=E_, layers=layers, ei=ei, w=w, x=x,
+                gen_s=time.time() - t0)
+
+
+# ----------------------------------------------------------------------------- CPU port
+def cpu_port_setup(inp):
+    from oracle import oracle as O
+    row_ptr, col, cum = O.c_csr_build(inp["ei"], inp["w"], inp["M"] + inp["U"], 1)
+    torch.manual_seed(0)
+    from mre_b200.model.pinsage import PinSage
+    sd = {k: v.detach().numpy() for k, v in
+          PinSage(inp["F"], inp["H"], inp["E"], inp["layers"]).state_dict().items()}
+    return dict(O=O, csr=(row_ptr, col, cum), sd=sd, threads=O.c_oracle().orc_max_threads())
+
+
+def cpu_port_step(inp, cp, sample, step):
+    """Embeds the first `sample` items as a self-contained catalogue: same per-item work as the
+    full job (W*L walk steps on the full graph, the same dense FLOPs per row)."""
+    O = cp["O"]
+    row_ptr, col, cum = cp["csr"]
+    nbrs, wts = [], []
+    for layer in range(inp["layers"]):
+        o = O.c_walk_topt(row_ptr, col, cum, np.arange(sample), 100, 2, 10, 1234,
+                          epoch=step * inp["layers"] + layer, num_threads=0)
+        nv = o["nvalid"]
+        nbrs.append([o["ids"][r, :nv[r]].tolist() for r in range(sample)])
+        wts.append([o["w64"][r, :nv[r]].tolist() for r in range(sample)])
+    return O.pinsage_forward(inp["x"][:sample].numpy(), cp["sd"], inp["layers"], nbrs, wts,
+                             dtype=np.float32)
+
+
+def run_cpu_port(inp, sample, steps, warmup):
+    cp = cpu_port_setup(inp)
+    sample = min(sample, inp["M"])
+    for s in range(warmup):
+        cpu_port_step(inp, cp, sample, s)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        cpu_port_step(inp, cp, sample, warmup + s)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=sample / dt, unit=UNIT, cores=cp["threads"], kind="port",
+                sample=f"{sample} of {inp['M']} start items per step (walks on the full graph, "
+                       f"W=100 L=2 T=10, {inp['layers']} layers + forward on those rows); items/s "
+                       "extrapolates linearly; C walk port on all host threads + numpy fp32 forward",
+                ms_per_step=dt * 1e3)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    inp = build_inputs(args.workload)
+    r = run_cpu_port(inp, args.cpu_sample, args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, inp, 1),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, inp, n_gpus):
+    return {"workload": f"{args.workload}: ML-25M-shaped synthetic graph" if args.workload == "C2"
+            else f"{args.workload}: tiny synthetic graph",
+            "items": inp["M"], "users": inp["U"], "ratings": inp["R"],
+            "dims": [inp["F"], inp["H"], inp["E"]], "layers": inp["layers"], "num_walks": 100,
+            "walk_length": 2, "num_neighbors": 10, "parallelism": f"rows/{n_gpus}"}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main_b200(args):
+    import torch.distributed as dist
+    import mre_b200  # noqa: F401
+    from mre_b200 import _native as N, kernels as K, neighbor_lists as NL, sharding as SH
+    from mre_b200.utils.random_walk import RandomWalkSampler
+    from mre_b200.model.pinsage import PinSage
+
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    inp = build_inputs(args.workload)
+    M, T, layers = inp["M"], 10, inp["layers"]
+    t0 = time.perf_counter()
+    sampler = RandomWalkSampler(torch.from_numpy(inp["ei"]), torch.from_numpy(inp["w"]), 2, 100,
+                                seed=1234, device=dev, num_nodes=M + inp["U"])
+    torch.cuda.synchronize()
+    csr_s = time.perf_counter() - t0
+    torch.manual_seed(0)
+    model = PinSage(inp["F"], inp["H"], inp["E"], layers).to(dev).eval()
+    model.precision = N.PREC_TF32 if args.precision == "tf32" else N.PREC_FP32
+    lo, hi = SH.shard_range(M, rank, ws)
+    x_host = inp["x"][lo:hi].contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty((hi - lo, inp["E"]), dtype=torch.float32).pin_memory()
+    nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(walk_events=None):
+        if ws > 1:
+            return SH.get_embeddings_sharded(model, x_dev, sampler, M, T)
+        batches = []
+        for layer in range(layers):
+            if walk_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e0.record()
+            ids, _c, w, nv = sampler._sample(nodes, T, check=False)
+            if walk_events is not None:
+                e1 = torch.cuda.Event(enable_timing=True); e1.record()
+                walk_events.append((e0, e1))
+            batches.append(NL.from_walk(ids, w, nv))
+        return model.forward(x_dev, None, batches, None)
+
+    def step_e2e():
+        if ws > 1:
+            emb = SH.get_embeddings_sharded(model, x_host, sampler, M, T)
+            out_host.copy_(emb, non_blocking=True)
+        else:
+            model.get_embeddings(x_host, sampler, T, out=out_host)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device(); step_e2e()
+    barrier()
+
+    # ---- timed: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
+    walk_events, step_ms = [], []
+    launches0 = N.launch_count()
+    clocks.active = True
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_device(walk_events)
+        b.record()
+        step_ms.append((a, b))
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    launches = N.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in step_ms)
+    walk_ms = [a.elapsed_time(b) for a, b in walk_events]
+
+    # ---- timed: end to end through the public API with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks.active = False
+    clocks.stop_flag = True
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = t.tolist()
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
+    value = M * args.steps / (dev_ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "config": dict(workload_config(args, inp, ws), l2="flushed between steps (256 MB "
+                           "write); CSR 0.6 GB exceeds the 126 MB L2",
+                           weights="seeded default init (torch.manual_seed(0))",
+                           csr_build_s=round(csr_s, 3), graph_gen_s=round(inp["gen_s"], 1),
+                           csr_bytes=sampler.csr.nbytes(), wall_s_timed_region=round(wall_dev, 4)),
+            "e2e": {"value": M * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks.summary()}
+
+    # ---- roofline of the dominant kernel (walk/count/top-T) ----
+    if ws == 1 and walk_ms:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        ids, _c, _w, _nv, trace = K.walk_topt(sampler.csr, nodes, 100, 2, T, 1234, 0, return_trace=True)
+        deg = (sampler.csr.row_ptr[1:] - sampler.csr.row_ptr[:-1])
+        cur = torch.cat([nodes.view(-1, 1, 1).expand(-1, 100, 1), trace[:, :, :-1]], dim=2).long()
+        executed = trace >= 0
+        d = deg[cur.clamp_min(0)].double()
+        per_step = 16 + 4 * torch.ceil(torch.log2(d + 1)) + 4
+        algo_bytes = float((per_step * executed).sum()) + M * (4 + 12 * T)
+        avg_ms = float(np.mean(walk_ms))
+        achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line["roofline"] = {"kernel": "walk_topt_kernel", "bound": "hbm", "achieved": achieved,
+                            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes,
+                            "avg_launch_ms": avg_ms, "executed_steps": int(executed.sum()),
+                            "share_of_step": sum(walk_ms) / dev_ms}
+    if ws == 1 and not args.no_cpu_baseline:
+        r = run_cpu_port(inp, args.cpu_sample, 3, 1)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

@@ -96,9 +96,11 @@ class PinSage(nn.Module):
         return hit[1], hit[2]
 
     # ---- forward ---------------------------------------------------------------------------
-    def forward(self, x, edge_index=None, sampled_neighbors=None, importance_weights=None):
+    def forward(self, x, edge_index=None, sampled_neighbors=None, importance_weights=None, *,
+                out=None):
         """reference model/pinsage.py:186-251.  ``sampled_neighbors`` / ``importance_weights``:
-        the reference's per-layer python lists, or a list of NeighborBatch (weights ignored)."""
+        the reference's per-layer python lists, or a list of NeighborBatch (weights ignored).
+        ``out``: optional (pinned) host or device tensor that receives the embeddings."""
         if edge_index is not None:
             raise NotImplementedError("the edge_index / torch_geometric branch (reference "
                                       "model/pinsage.py:243-245) is outside the B200 hot path")
@@ -141,23 +143,47 @@ class PinSage(nn.Module):
                                        lists=nb.as_args(), pool_mode=N.POOL_PINSAGE,
                                        flags=N.EPI_RELU | N.EPI_L2NORM, precision=prec)
         emb = K.gather_dense(h, *P(self.output_proj), flags=N.EPI_L2NORM, precision=prec)  # :248-249
+        if out is not None:
+            out.copy_(emb, non_blocking=True)
+            if not out.is_cuda:
+                torch.cuda.current_stream(dev).synchronize()
+            return out
         return emb if in_dev.type == "cuda" else emb.to(in_dev)
 
-    def get_embeddings(self, x, random_walk_sampler, num_neighbors=10):
+    def get_embeddings(self, x, random_walk_sampler, num_neighbors=10, *, out=None):
         """reference model/pinsage.py:253-280: resample neighbours per layer, then forward.
         With this package's sampler everything stays on the device (NeighborBatch); any other
-        sampler object goes through its list API exactly like the reference."""
+        sampler object goes through its list API exactly like the reference.  A pinned host
+        ``x`` is uploaded on a side stream while the walk kernels (which do not need the
+        features) run; ``out`` optionally receives the embeddings (pinned host or device)."""
         M = x.size(0)
         if hasattr(random_walk_sampler, "batch_sample_neighbors_tensor"):
             dev = self._device()
-            nodes = torch.arange(M, dtype=torch.int32, device=dev)
             if M > random_walk_sampler.csr.num_nodes:
                 raise IndexError("list index out of range")
+            in_dev = x.device
+            main = torch.cuda.current_stream(dev)
+            if not x.is_cuda and x.is_pinned():
+                if getattr(self, "_copy_stream", None) is None:
+                    self._copy_stream = torch.cuda.Stream(dev)
+                with torch.cuda.stream(self._copy_stream):
+                    xd = x.to(dev, dtype=torch.float32, non_blocking=True)
+                    uploaded = torch.cuda.Event()
+                    uploaded.record(self._copy_stream)
+                xd.record_stream(main)
+            else:
+                xd, uploaded = x, None
+            nodes = torch.arange(M, dtype=torch.int32, device=dev)
             batches = []
             for _ in range(self.num_layers):
                 ids, _c, w, nv = random_walk_sampler._sample(nodes, num_neighbors, check=False)
                 batches.append(NL.from_walk(ids, w, nv))
-            return self.forward(x, None, batches, None)
+            if uploaded is not None:
+                main.wait_event(uploaded)
+            emb = self.forward(xd, None, batches, None, out=out)
+            if out is not None or in_dev.type == "cuda":
+                return emb
+            return emb.to(in_dev)
         all_n, all_w = [], []
         nodes = list(range(M))
         for _ in range(self.num_layers):

@@ -368,14 +368,18 @@ def l2_normalize(v, eps=1e-12):
     return (v / np.maximum(n, eps)).astype(np.float32)
 
 
-def linear(x, W, b):
-    return (x.astype(np.float64) @ W.astype(np.float64).T + b.astype(np.float64))
+def linear(x, W, b, dtype=np.float64):
+    return (x.astype(dtype) @ W.astype(dtype).T + b.astype(dtype))
 
 
-def pinsage_forward(x, sd, num_layers, sampled_neighbors=None, importance_weights=None):
+def pinsage_forward(x, sd, num_layers, sampled_neighbors=None, importance_weights=None,
+                    dtype=np.float64):
     """model/pinsage.py:186-251 with edge_index=None.  sd: state_dict of numpy arrays
-    (reference key names).  Accumulates in float64, returns float32: the oracle is the
-    'true' value both the torch reference and the CUDA path are compared against."""
+    (reference key names).  Accumulates in float64 by default and returns float32: the oracle
+    is the 'true' value both the torch reference and the CUDA path are compared against
+    (dtype=np.float32 is the reference's own arithmetic, used for the CPU-baseline timing)."""
+    import functools
+    linear = functools.partial(globals()["linear"], dtype=dtype)
     h = np.maximum(linear(np.asarray(x, np.float32), sd["input_proj.weight"],
                           sd["input_proj.bias"]), 0).astype(np.float32)          # :202
     if sampled_neighbors is None or importance_weights is None:                   # :205-214

@@ -121,5 +121,7 @@ def test_sampler_dropin_api(K):
     assert adj[0] == e0                                                   # edge order preserved
     with pytest.raises(IndexError):
         s.sample_neighbors(10**6)
-    empty_n, empty_w = s.sample_neighbors(len(adj) - 1)                   # node without out-edges
-    assert empty_n == [] and empty_w == []
+    for lonely in (420, 422):             # sink (in-edges only) and isolated node of the fixture
+        assert adj[lonely] == []
+        empty_n, empty_w = s.sample_neighbors(lonely)
+        assert empty_n == [] and empty_w == []
