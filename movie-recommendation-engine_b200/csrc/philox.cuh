@@ -1,5 +1,5 @@
 // philox.cuh -- Philox4x32-10 (Salmon et al., SC'11) and the 53-bit uniform recipe shared
-// with oracle/walk_oracle.c.  Counter-based: the draw for (start, walk, step) does not
+// with the CPU checker used by tests/.  Counter-based: the draw for (start, walk, step) does not
 // depend on launch geometry, call order or sharding.
 #pragma once
 #include <stdint.h>

@@ -55,9 +55,10 @@ def all_gather_cols(local, group=None):
     rank, ws = world(group)
     if ws == 1:
         return local
-    out = torch.empty((ws,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    nq, c = local.shape
+    out = torch.empty((ws * nq, c), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out.permute(1, 0, 2).reshape(local.size(0), ws * local.size(1)).contiguous()
+    return out.view(ws, nq, c).permute(1, 0, 2).reshape(nq, ws * c).contiguous()
 
 
 def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None):
