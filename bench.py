@@ -285,7 +285,7 @@ def main_b200(args):
                            "write); CSR 0.6 GB exceeds the 126 MB L2",
                            weights="seeded default init (torch.manual_seed(0))",
                            csr_build_s=round(csr_s, 3), graph_gen_s=round(inp["gen_s"], 1),
-                           csr_bytes=sampler.csr.nbytes(), wall_s_timed_region=round(wall_dev, 4)),
+                           csr_bytes=sampler.csr.nbytes(), walk_index_bytes=sampler.csr.index_nbytes(), wall_s_timed_region=round(wall_dev, 4)),
             "e2e": {"value": M * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                     "ms_per_step": e2e_s / args.steps * 1e3},

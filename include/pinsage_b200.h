@@ -88,6 +88,29 @@ int pb200_walk_topt(const int64_t* row_ptr, const int32_t* col, const void* cum,
                     int32_t* out_ids, int32_t* out_counts, float* out_weights,
                     int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream);
 
+/* Sampling index over the CSR (uint32-quanta graphs): an implicit 8-ary search tree per row
+ * whose nodes are single 256-bit loads -- meta uint32 [4*N] {leaf block offset, degree, row
+ * total, upper-level block offset}, leaf uint32 [16 * leaf_blocks] {8 cumulative weights | 8
+ * neighbour ids}, idx uint32 [8 * idx_blocks] separator keys (top level first).  It selects
+ * exactly the edge the flat search selects; a step costs ~3 dependent loads and one DRAM
+ * access instead of ~log2(degree).
+ *   1. pb200_walk_index_sizes: sizes_out int64 [2] = {leaf_blocks, idx_blocks} (device);
+ *      offsets are left in `workspace` for step 2 (same buffer, unmodified in between);
+ *   2. the caller allocates meta / idx (32 B aligned) / leaf (64 B aligned);
+ *   3. pb200_walk_index_build fills them. */
+size_t pb200_walk_index_workspace_bytes(int64_t num_nodes);
+int pb200_walk_index_sizes(const int64_t* row_ptr, int64_t num_nodes, int64_t* sizes_out,
+                           void* workspace, size_t workspace_bytes, pb200_stream_t stream);
+int pb200_walk_index_build(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                           int64_t num_nodes, const void* workspace, uint32_t* meta, uint32_t* idx,
+                           uint32_t* leaf, pb200_stream_t stream);
+/* pb200_walk_topt on the sampling index (same outputs, bit-identical results). */
+int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx, const uint32_t* leaf,
+                            int64_t num_nodes, const int32_t* starts, int64_t n, int num_walks,
+                            int walk_length, int num_neighbors, uint64_t seed, uint32_t epoch,
+                            int32_t* out_ids, int32_t* out_counts, float* out_weights,
+                            int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream);
+
 /* Counting stage alone, given traces (parity "given the same walk traces"):
  * trace int32 [n, V] (V = W*L visits in walk-major order, -1 = none). */
 int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_start, int num_neighbors,

@@ -30,6 +30,13 @@ SIGNATURES = {
                                 c_ptr, c_size, c_ptr]),
     "pb200_walk_topt": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_int,
                                 c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pb200_walk_index_workspace_bytes": (c_size, [c_i64]),
+    "pb200_walk_index_sizes": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
+    "pb200_walk_index_build": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       c_ptr]),
+    "pb200_walk_topt_indexed": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
+                                        c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                        c_ptr]),
     "pb200_count_topt": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pb200_pool": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int,
                            c_ptr, c_ptr]),

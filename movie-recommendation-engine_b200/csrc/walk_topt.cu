@@ -10,6 +10,8 @@
 //     Counter + stable sorted() order (random_walk.py:101-107) -- and emits
 //     weight = count / sum(kept counts) (random_walk.py:113-115).
 // Bound by HBM latency/bandwidth: per step ~ (row_ptr pair + log2(deg) prefix probes + col).
+#include <type_traits>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -23,6 +25,9 @@ struct WalkParams {
     const void* __restrict__ cum;
     const int32_t* __restrict__ starts;
     const int32_t* __restrict__ trace_in;  // count-only mode: [n, V]
+    const uint4* __restrict__ meta;        // indexed mode (walk_index.cu)
+    const uint32_t* __restrict__ idx;
+    const uint32_t* __restrict__ leaf;
     int64_t n;
     int64_t num_nodes;
     int W, L, T;
@@ -77,9 +82,76 @@ __device__ __forceinline__ int64_t pick_edge(const double* __restrict__ cum, int
     return lo;
 }
 
-// CumT = uint32_t / double: walk mode.  CumT = void handled by kCountOnly.
-template <typename CumT, bool kCountOnly>
+// ---- indexed step (walk_index.cu): every tree node is one 256-bit load ----
+struct U8 { uint32_t v[8]; };
+
+__device__ __forceinline__ U8 ld256_keep(const uint32_t* p) {   // upper levels: keep in L2
+    U8 r;
+    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                   "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ U8 ld256_stream(const uint32_t* p) { // leaves: streamed through L2
+    U8 r;
+    asm volatile("ld.global.nc.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                   "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t count_le(const U8& k, uint32_t t) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c += (k.v[i] <= t);
+    return c;
+}
+
+constexpr int kMaxUpper = 7;   // degree < 8^8
+
+// Returns the next node (>= 0) or -1 at a dead end.  Same rule as pick_edge: first edge whose
+// cumulative weight exceeds t = floor(k53 * total / 2^53).
+__device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
+                                            const uint32_t* __restrict__ idx,
+                                            const uint32_t* __restrict__ leaf, int cur,
+                                            uint64_t k53) {
+    const uint4 m = __ldg(meta + cur);   // {leaf block offset, degree, total, idx block offset}
+    if (m.y == 0u) return -1;
+    const uint64_t total = m.z;
+    const uint64_t t64 = (__umul64hi(k53, total) << 11) | ((k53 * total) >> 53);
+    const uint32_t t = (uint32_t)t64;
+    uint32_t nbl[kMaxUpper + 1];
+    nbl[0] = (m.y + 7u) >> 3;
+    int L = 0;
+#pragma unroll
+    for (int l = 1; l <= kMaxUpper; ++l) {
+        nbl[l] = (nbl[l - 1] + 7u) >> 3;
+        L += (nbl[l - 1] > 1u);
+    }
+    uint32_t pos = 0, off = m.w;
+#pragma unroll
+    for (int l = kMaxUpper; l >= 1; --l) {
+        if (l <= L) {
+            const U8 k = ld256_keep(idx + ((size_t)(off + pos) << 3));
+            pos = pos * 8u + count_le(k, t);
+            off += nbl[l];
+        }
+    }
+    const uint32_t* blk = leaf + ((size_t)(m.x + pos) << 4);
+    const U8 keys = ld256_stream(blk);
+    const U8 cols = ld256_stream(blk + 8);
+    const uint32_t c = count_le(keys, t);
+    uint32_t next = cols.v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) next = (c == (uint32_t)i) ? cols.v[i] : next;
+    return (int)next;
+}
+
+enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3 };
+
+template <int kMode>
 __global__ void __launch_bounds__(256) walk_topt_kernel(const WalkParams p) {
+    constexpr bool kCountOnly = kMode == kCountTrace;
+    using CumT = typename std::conditional<kMode == kFlatF64, double, uint32_t>::type;
     extern __shared__ int32_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -117,14 +189,18 @@ __global__ void __launch_bounds__(256) walk_topt_kernel(const WalkParams p) {
                                           p.epoch, p.seed_lo, p.seed_hi);
                     int next = -1;
                     if (active) {
-                        const int64_t r0 = __ldg(p.row_ptr + cur);
-                        const int64_t r1 = __ldg(p.row_ptr + cur + 1);
-                        if (r1 == r0) {
+                        const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
+                                                     : uniform53(r.v[0], r.v[1]);
+                        if (kMode == kIndexed) {
+                            next = indexed_step(p.meta, p.idx, p.leaf, cur, k53);
+                        } else {
+                            const int64_t r0 = __ldg(p.row_ptr + cur);
+                            const int64_t r1 = __ldg(p.row_ptr + cur + 1);
+                            if (r1 != r0) next = __ldg(p.col + pick_edge(cum, r0, r1, k53));
+                        }
+                        if (next < 0) {
                             active = false;  // dead end: random_walk.py:68-69
                         } else {
-                            const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
-                                                         : uniform53(r.v[0], r.v[1]);
-                            next = __ldg(p.col + pick_edge(cum, r0, r1, k53));
                             cur = next;
                             table_insert(keys, cnt, first, p.slots, p.slot_shift, next,
                                          (uint32_t)(walk * p.L + l));
@@ -197,9 +273,9 @@ static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_
         return PB200_ERR_UNSUPPORTED;
     }
     const size_t smem = per_warp * warps;
-    auto kern = count_only ? walk_topt_kernel<uint32_t, true>
-              : cum_kind == 0 ? walk_topt_kernel<uint32_t, false>
-                              : walk_topt_kernel<double, false>;
+    auto kern = count_only ? walk_topt_kernel<kCountTrace>
+              : p.meta ? walk_topt_kernel<kIndexed>
+              : cum_kind == 0 ? walk_topt_kernel<kFlatU32> : walk_topt_kernel<kFlatF64>;
     if (smem > 48 * 1024)
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // enough blocks to fill every SM several times; grid-stride over the rest
@@ -251,4 +327,28 @@ extern "C" int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_
     p.out_ids = out_ids; p.out_counts = out_counts; p.out_w = out_weights;
     p.out_nvalid = out_nvalid;
     return launch_walk(p, 0, true, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx,
+                                       const uint32_t* leaf, int64_t num_nodes,
+                                       const int32_t* starts, int64_t n, int num_walks,
+                                       int walk_length, int num_neighbors, uint64_t seed,
+                                       uint32_t epoch, int32_t* out_ids, int32_t* out_counts,
+                                       float* out_weights, int32_t* out_nvalid, int32_t* trace_out,
+                                       pb200_stream_t stream) {
+    PB_REQUIRE(n >= 0 && num_walks > 0 && walk_length > 0 && num_neighbors > 0,
+               "walk_topt_indexed: n=%lld W=%d L=%d T=%d must be positive", (long long)n,
+               num_walks, walk_length, num_neighbors);
+    PB_REQUIRE((int64_t)num_walks * walk_length <= 65535,
+               "walk_topt_indexed: num_walks*walk_length must be <= 65535");
+    if (n == 0) return PB200_OK;
+    PB_REQUIRE(meta && leaf && starts && out_ids && out_counts && out_weights && out_nvalid,
+               "walk_topt_indexed: null pointer");
+    WalkParams p{};
+    p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
+    p.n = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.epoch = epoch;
+    p.out_ids = out_ids; p.out_counts = out_counts; p.out_w = out_weights;
+    p.out_nvalid = out_nvalid; p.trace_out = trace_out;
+    return launch_walk(p, 0, false, (cudaStream_t)stream);
 }

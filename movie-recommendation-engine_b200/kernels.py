@@ -7,6 +7,7 @@ unless a host-side flag has to be read (build-time only).
 from __future__ import annotations
 
 from dataclasses import dataclass
+from typing import Optional
 
 import torch
 
@@ -24,6 +25,10 @@ class CSR:
     quant_shift: int           # weights were multiplied by 2**quant_shift (cum_kind 0)
     num_nodes: int
     num_edges: int
+    # sampling index (8-ary search tree per row; uint32-quanta graphs only)
+    meta: Optional[torch.Tensor] = None     # int32 [N, 4]
+    idx: Optional[torch.Tensor] = None      # int32 [idx_blocks, 8]
+    leaf: Optional[torch.Tensor] = None     # int32 [leaf_blocks, 16]
 
     @property
     def device(self):
@@ -32,8 +37,47 @@ class CSR:
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.row_ptr, self.col, self.cum))
 
+    def index_nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.meta, self.idx, self.leaf)
+                   if t is not None)
 
-def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_float=False):
+
+def _aligned_empty(n_int32, align, dev):
+    """int32 buffer whose data pointer is `align`-byte aligned (torch gives >= 256 B for fresh
+    allocations; asserted rather than assumed)."""
+    t = torch.empty(max(n_int32, 1), dtype=torch.int32, device=dev)
+    assert t.data_ptr() % align == 0
+    return t
+
+
+def build_walk_index(csr):
+    """Adds the 8-ary sampling index to a uint32-quanta CSR (pb200_walk_index_*)."""
+    if csr.cum_kind != 0 or csr.num_nodes == 0:
+        return csr
+    dev = csr.device
+    st = stream_ptr(dev)
+    Nn = csr.num_nodes
+    ws_bytes = lib().pb200_walk_index_workspace_bytes(Nn)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    sizes = torch.zeros(2, dtype=torch.int64, device=dev)
+    check(lib().pb200_walk_index_sizes(ptr(csr.row_ptr), Nn, ptr(sizes), ptr(ws), ws_bytes, st),
+          "walk_index_sizes")
+    leaf_blocks, idx_blocks = sizes.tolist()          # build-time sync
+    meta = _aligned_empty(4 * Nn, 16, dev)
+    idx = _aligned_empty(8 * max(idx_blocks, 1), 32, dev)
+    leaf = _aligned_empty(16 * max(leaf_blocks, 1), 64, dev)
+    check(lib().pb200_walk_index_build(ptr(csr.row_ptr), ptr(csr.col),
+                                       ptr(csr.cum) if csr.num_edges else ptr(csr.row_ptr), Nn,
+                                       ptr(ws), ptr(meta), ptr(idx), ptr(leaf), st),
+          "walk_index_build")
+    csr.meta = meta.view(Nn, 4)
+    csr.idx = idx.view(-1, 8)[:idx_blocks]
+    csr.leaf = leaf.view(-1, 16)[:leaf_blocks]
+    return csr
+
+
+def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_float=False,
+              index=True):
     dev = N.device_of(edge_index, edge_weights, device=device)
     ei = N.dev_tensor(edge_index, torch.int64, dev)
     if ei.dim() != 2 or ei.size(0) != 2:
@@ -79,11 +123,12 @@ def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_
             raise ValueError(f"{zero_rows} nodes have out-edges whose weights sum to zero "
                              "(the reference's np.random.choice would raise on NaN probabilities)")
         break
-    return CSR(row_ptr, col, cum, 0 if quant_shift >= 0 else 1, quant_shift, num_nodes, E)
+    csr = CSR(row_ptr, col, cum, 0 if quant_shift >= 0 else 1, quant_shift, num_nodes, E)
+    return build_walk_index(csr) if index else csr
 
 
 def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epoch=0,
-              return_trace=False):
+              return_trace=False, use_index=True):
     dev = csr.device
     s = N.dev_tensor(starts, torch.int32, dev)
     n = s.numel()
@@ -94,6 +139,15 @@ def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epo
     nvalid = torch.empty(n, dtype=torch.int32, device=dev)
     trace = torch.empty((n, num_walks, walk_length), dtype=torch.int32, device=dev) \
         if return_trace else None
+    if use_index and csr.meta is not None:
+        check(lib().pb200_walk_topt_indexed(ptr(csr.meta), ptr(csr.idx), ptr(csr.leaf),
+                                            csr.num_nodes, ptr(s), n, int(num_walks),
+                                            int(walk_length), T, int(seed) & (2**64 - 1),
+                                            int(epoch) & 0xFFFFFFFF, ptr(ids), ptr(counts),
+                                            ptr(weights), ptr(nvalid), ptr(trace), stream_ptr(dev)),
+              "walk_topt_indexed")
+        return (ids, counts, weights, nvalid, trace) if return_trace else \
+            (ids, counts, weights, nvalid)
     check(lib().pb200_walk_topt(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cum) if csr.num_edges else
                                 ptr(csr.row_ptr), csr.cum_kind, csr.num_nodes, ptr(s), n,
                                 int(num_walks), int(walk_length), T, int(seed) & (2**64 - 1),

@@ -35,8 +35,13 @@ def test_csr_and_walk_match_reference_golden(K, name):
     np.testing.assert_array_equal(_np(csr.col), col)
     got_cum = _np(csr.cum).view(np.uint32) if qs >= 0 else _np(csr.cum)
     np.testing.assert_array_equal(got_cum, cum)
+    assert (csr.meta is not None) == (qs >= 0)        # sampling index on quantised graphs
+    flat = K.walk_topt(csr, torch.from_numpy(c["starts"]), c["W"], c["L"], c["T"], c["seed"],
+                       c["epoch"], return_trace=True, use_index=False)
     ids, counts, w32, nvalid, trace = K.walk_topt(csr, torch.from_numpy(c["starts"]), c["W"], c["L"],
                                                   c["T"], c["seed"], c["epoch"], return_trace=True)
+    for a, b in zip(flat, (ids, counts, w32, nvalid, trace)):   # indexed == flat search, bitwise
+        np.testing.assert_array_equal(_np(a), _np(b))
     # vs the UNMODIFIED reference driven by the same uniforms
     np.testing.assert_array_equal(_np(nvalid), c["nvalid"])
     np.testing.assert_array_equal(_np(ids).astype(np.int64), c["ids"])
@@ -62,7 +67,8 @@ def test_walk_c1_full_vs_oracle(K):
     np.testing.assert_array_equal(_np(csr.row_ptr), row_ptr)
     np.testing.assert_array_equal(_np(csr.cum).view(np.uint32), cum)
     for epoch in range(2):
-        ids, counts, w32, nvalid = K.walk_topt(csr, torch.arange(M), 100, 2, 10, 1234, epoch)
+        ids, counts, w32, nvalid = K.walk_topt(csr, torch.arange(M), 100, 2, 10, 1234, epoch,
+                                               use_index=bool(epoch))
         o = O.c_walk_topt(row_ptr, col, cum, np.arange(M), 100, 2, 10, 1234, epoch)
         np.testing.assert_array_equal(_np(ids), o["ids"])
         np.testing.assert_array_equal(_np(counts), o["counts"])
@@ -125,3 +131,49 @@ def test_sampler_dropin_api(K):
         assert adj[lonely] == []
         empty_n, empty_w = s.sample_neighbors(lonely)
         assert empty_n == [] and empty_w == []
+
+
+def test_walk_index_structure_and_deep_rows(K):
+    """The 8-ary sampling index: block layout vs a numpy restatement, and rows deep enough for
+    3-4 tree levels (degree up to 5000) searched identically to the flat binary search."""
+    rng = np.random.Generator(np.random.PCG64(3))
+    degs = [0, 1, 7, 8, 9, 63, 64, 65, 511, 512, 513, 4097, 5000]
+    src = np.concatenate([np.full(d, v) for v, d in enumerate(degs)]).astype(np.int64)
+    N = 6000
+    dst = rng.integers(0, len(degs), size=src.size).astype(np.int64)
+    w = (0.5 * rng.integers(0, 11, size=src.size)).astype(np.float32)      # zero weights allowed
+    w[np.cumsum(degs)[1:] - 1] = 2.5                                        # rows keep a positive total
+    perm = rng.permutation(src.size)                                        # edge order != row order
+    ei = np.stack([src[perm], dst[perm]])
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w[perm]), num_nodes=N)
+    row_ptr, col, cum = O.csr_build(ei, w[perm], N, 1)
+    meta = _np(csr.meta).view(np.uint32); leaf = _np(csr.leaf).view(np.uint32); idx = _np(csr.idx).view(np.uint32)
+    lo = io = 0
+    for v, d in enumerate(degs):
+        a = row_ptr[v]
+        nb0 = (d + 7) // 8
+        assert meta[v].tolist() == [lo, d, int(cum[a + d - 1]) if d else 0, io]
+        keys = np.full(nb0 * 8, 0xFFFFFFFF, np.uint32); keys[:d] = cum[a:a + d]
+        cols = np.full(nb0 * 8, 0xFFFFFFFF, np.uint32); cols[:d] = col[a:a + d].view(np.uint32)
+        np.testing.assert_array_equal(leaf[lo:lo + nb0, :8].reshape(-1), keys)
+        np.testing.assert_array_equal(leaf[lo:lo + nb0, 8:].reshape(-1), cols)
+        levels, nb = [], nb0
+        while nb > 1:
+            levels.append(nb); nb = (nb + 7) // 8
+        off = io
+        for l in range(len(levels), 0, -1):               # top level first
+            nkeys, nblk = levels[l - 1], (levels[l - 1] + 7) // 8
+            want = np.full(nblk * 8, 0xFFFFFFFF, np.uint32)
+            last = np.minimum(8 ** l * (np.arange(nkeys) + 1), d) - 1
+            want[:nkeys] = cum[a + last]
+            np.testing.assert_array_equal(idx[off:off + nblk].reshape(-1), want)
+            off += nblk
+        lo += nb0; io = off
+    assert leaf.shape[0] == lo and idx.shape[0] == io
+    starts = np.arange(len(degs))
+    got = K.walk_topt(csr, torch.from_numpy(starts), 200, 3, 20, 77, 0, return_trace=True)
+    flat = K.walk_topt(csr, torch.from_numpy(starts), 200, 3, 20, 77, 0, return_trace=True, use_index=False)
+    o = O.c_walk_topt(row_ptr, col, cum, starts, 200, 3, 20, 77, 0, return_trace=True)
+    for a, b, key in zip(got, flat, ["ids", "counts", "w32", "nvalid", "trace"]):
+        np.testing.assert_array_equal(_np(a), _np(b))
+        np.testing.assert_array_equal(_np(a), o[key])
