@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--workload", default="C2", choices=["C1", "C2"])
     ap.add_argument("--cpu-sample", type=int, default=8192, help="start items per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="auto", choices=["fp32", "tf32", "auto"])
     return ap.parse_args()
 
 
@@ -198,7 +198,7 @@ def main_b200(args):
     csr_s = time.perf_counter() - t0
     torch.manual_seed(0)
     model = PinSage(inp["F"], inp["H"], inp["E"], layers).to(dev).eval()
-    model.precision = N.PREC_TF32 if args.precision == "tf32" else N.PREC_FP32
+    model.precision = N.PRECISIONS[args.precision]
     lo, hi = SH.shard_range(M, rank, ws)
     x_host = inp["x"][lo:hi].contiguous().pin_memory()
     x_dev = x_host.to(dev)
@@ -280,7 +280,7 @@ def main_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "dtype": "f32" if args.precision == "fp32" else "tf32 (fp32 accumulate; walks: u32/u64 integer)", "data": "synthetic",
             "config": dict(workload_config(args, inp, ws), l2="flushed between steps (256 MB "
                            "write); CSR 0.6 GB exceeds the 126 MB L2",
                            weights="seeded default init (torch.manual_seed(0))",

@@ -151,13 +151,15 @@ int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
  *                    of pb200_pool (model/pinsage.py:232-240).
  *   flags: PB200_EPI_RELU, PB200_EPI_L2NORM (F.normalize eps 1e-12), PB200_EPI_LAYERNORM
  *   (gamma/beta = ln_gamma/ln_beta, eps 1e-5; aggregators.py:276-283).
- *   precision: PB200_PREC_FP32 (CUDA-core FMA) or PB200_PREC_TF32 (tcgen05 kind::tf32).
+ *   precision: PB200_PREC_FP32 / PB200_PREC_TF32 / PB200_PREC_AUTO (below).  The tensor-core
+ *   path covers n_out <= 256, k1 % 4 == k2 % 4 == 0, 16-byte aligned operands, no LayerNorm.
  * ------------------------------------------------------------------------------------ */
 #define PB200_EPI_RELU 1
 #define PB200_EPI_L2NORM 2
 #define PB200_EPI_LAYERNORM 4
-#define PB200_PREC_FP32 0
-#define PB200_PREC_TF32 1
+#define PB200_PREC_FP32 0 /* CUDA-core fp32 FMA (exact-fp32 reference kernel) */
+#define PB200_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM; UNSUPPORTED if the shape is not covered */
+#define PB200_PREC_AUTO 2 /* TF32 tensor cores where the shape is covered, CUDA-core fp32 otherwise */
 
 int pb200_gather_dense(const float* a1, int k1, const float* a2, int k2, const float* pool_x,
                        int64_t pool_rows, const int32_t* ids, const float* weights,

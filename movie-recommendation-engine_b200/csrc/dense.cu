@@ -12,24 +12,11 @@
 // Tile: 32 rows x BN columns per 256-thread block, K in chunks of 32.  The A tile is built in
 // shared memory from A1 columns and, for the second half of K, either a dense A2 row or the
 // pooled neighbourhood row computed on the fly from the per-block (id, weight) lists.
-#include "pool.cuh"
+#include "dense.cuh"
 
 namespace pb200 {
 
 constexpr int BM = 32, BK = 32;
-
-struct DenseParams {
-    const float* __restrict__ a1; int k1;
-    const float* __restrict__ a2; int k2;
-    const float* __restrict__ pool_x;
-    ListArgs lists;
-    const float* __restrict__ w;      // [N, K]
-    const float* __restrict__ bias;   // [N] or null
-    const float* __restrict__ ln_gamma;
-    const float* __restrict__ ln_beta;
-    int64_t n; int n_out; int flags;
-    float* __restrict__ out;
-};
 
 template <int BN, bool kVec>
 __global__ void __launch_bounds__(256) dense_kernel(const DenseParams p) {
@@ -287,7 +274,6 @@ int gather_dense_fp32(const DenseParams& p0, cudaStream_t stream) {
 
 using namespace pb200;
 
-namespace pb200 { int gather_dense_tf32(const DenseParams& p, cudaStream_t stream); }
 
 extern "C" int pb200_gather_dense(const float* a1, int k1, const float* a2, int k2,
                                   const float* pool_x, int64_t pool_rows, const int32_t* ids,
@@ -313,7 +299,10 @@ extern "C" int pb200_gather_dense(const float* a1, int k1, const float* a2, int 
                        pool_rows};
     p.w = w; p.bias = bias; p.ln_gamma = ln_gamma; p.ln_beta = ln_beta;
     p.n = n; p.n_out = n_out; p.flags = flags; p.out = out;
-    if (precision == PB200_PREC_TF32) return gather_dense_tf32(p, (cudaStream_t)stream);
-    PB_REQUIRE(precision == PB200_PREC_FP32, "gather_dense: unknown precision %d", precision);
+    if (precision == PB200_PREC_TF32 ||
+        (precision == PB200_PREC_AUTO && n >= 64 && gather_dense_tf32_supported(p)))
+        return gather_dense_tf32(p, (cudaStream_t)stream);
+    PB_REQUIRE(precision == PB200_PREC_FP32 || precision == PB200_PREC_AUTO,
+               "gather_dense: unknown precision %d", precision);
     return gather_dense_fp32(p, (cudaStream_t)stream);
 }

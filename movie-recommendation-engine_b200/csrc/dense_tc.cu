@@ -1,12 +1,340 @@
-// dense_tc.cu -- tcgen05 (kind::tf32) path of pb200_gather_dense.  Placeholder until the
-// tensor-core kernel lands: reports UNSUPPORTED so callers fail loudly instead of silently
-// running something else.
-#include "pool.cuh"
+// dense_tc.cu -- tcgen05 (5th-gen tensor core, kind::tf32) path of pb200_gather_dense.
+//
+//   out[m,:] = epi( [A1[m,:K1] | A2row(m)] . W^T + bias ),  A2row dense or pooled on the fly
+//
+// One CTA per 128-row tile (UMMA M=128, N = n_out rounded up to 16 <= 256, K=8 per MMA):
+//   warps 0..15  producers: build the K-major, 128B-swizzled A tile ([h | sum_j w_j h[id_j]],
+//                16-byte vector loads, rounded to TF32 with cvt.rna) and the W tile in shared
+//                memory, S-stage ring, fence.proxy.async + mbarrier arrive per stage
+//   warp 16      one elected thread issues tcgen05.mma (accumulator in TMEM) and
+//                tcgen05.commit's each stage back to the producers
+//   warps 0..3   epilogue: tcgen05.ld (one output row per thread), bias, ReLU, row L2-norm from
+//                registers (no cross-thread reduction), staged through shared memory for
+//                coalesced 128 B stores
+// Operand tiles are written by ordinary st.shared with the swizzle applied by hand, so no TMA
+// descriptor is needed; the smem matrix descriptors follow the canonical K-major SWIZZLE_128B
+// layout (8 rows x 128 B atoms, SBO = 1024 B).
+#include "dense.cuh"
 
 namespace pb200 {
-struct DenseParams;
-int gather_dense_tf32(const DenseParams&, cudaStream_t) {
-    set_error("gather_dense: PB200_PREC_TF32 (tcgen05) path not built in this version");
-    return PB200_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int kProducerWarps = 16;
+constexpr int kProducers = kProducerWarps * 32;       // 512
+constexpr int kThreads = kProducers + 32;             // + MMA warp
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;                           // fp32 per 128-byte swizzle row
+constexpr int kABytes = kTileM * 128;                 // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float f) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (Blackwell: version = 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address (16 B units)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8-row group pitch
+    d |= (uint64_t)1 << 46;                          // descriptor version
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcGeom {
+    int umma_n;      // n_out rounded up to 16
+    int tmem_cols;   // power of two >= 32
+    int stages;
+    int b_bytes;     // umma_n * 128
+    int stage_bytes;
+    size_t smem_bytes;
+    size_t off_lists, off_bias, off_bars;
+};
+
+__host__ __device__ inline TcGeom geometry(int n_out, int T, bool pooled) {
+    TcGeom g{};
+    g.umma_n = (n_out + 15) / 16 * 16;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < g.umma_n) g.tmem_cols <<= 1;
+    g.b_bytes = g.umma_n * 128;
+    g.stage_bytes = kABytes + g.b_bytes;                        // multiples of 1024
+    const size_t lists = pooled ? (size_t)kTileM * (4 + (size_t)T * 8) : 0;
+    const size_t fixed = 1024 /*alignment slack*/ + lists + 256 * 4 /*bias*/ + 256 /*barriers*/;
+    int s = (int)((220 * 1024 - fixed) / g.stage_bytes);
+    g.stages = s > 4 ? 4 : s;
+    g.off_lists = (size_t)g.stages * g.stage_bytes;
+    g.off_bias = g.off_lists + lists;
+    g.off_bars = g.off_bias + 256 * 4;
+    g.smem_bytes = g.off_bars + 256 + 1024;
+    return g;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams p, const TcGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = p.lists.T;
+    const bool pooled = p.pool_x != nullptr && p.k2 > 0;
+    const int K = p.k1 + p.k2;
+    const int nchunks = (K + kChunkK - 1) / kChunkK;
+    const int64_t m0 = (int64_t)blockIdx.x * kTileM;
+
+    int* s_nv = reinterpret_cast<int*>(smem + g.off_lists);             // [128]
+    int* s_id = s_nv + kTileM;                                          // [128][T]
+    float* s_w = reinterpret_cast<float*>(s_id + (size_t)kTileM * T);   // [128][T]
+    float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);        // [256]
+    const uint32_t bars = sbase + (uint32_t)g.off_bars;
+    // barrier i: full[s] = bars + 8*s, empty[s] = bars + 8*(4+s), done = bars + 64, tmem ptr at +72
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bars + 72);
+
+    if (tid == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(bars + 8 * s, kProducers);
+            mbar_init(bars + 8 * (4 + s), 1);
+        }
+        mbar_init(bars + 64, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarps) {   // MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < 256) s_bias[tid] = (p.bias && tid < p.n_out) ? p.bias[tid] : 0.f;
+    if (pooled && warp < kProducerWarps) {
+        for (int r = warp; r < kTileM; r += kProducerWarps) {
+            const int64_t m = m0 + r;
+            int nv = 0;
+            if (m < p.n) nv = prepare_list(p.lists, m, s_id + r * T, s_w + r * T, lane);
+            if (lane == 0) s_nv[r] = nv;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kProducerWarps) {
+        // ===================== producers =====================
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % g.stages, u = c / g.stages;
+            const int k0 = c * kChunkK;
+            const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
+            const uint32_t b_s = a_s + kABytes;
+            // ---- issue the global loads of this chunk first (A: 2, B: up to 4 float4) ----
+            float4 av[2], bv[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + kProducers * i;
+                const int r = idx >> 3, k = k0 + (idx & 7) * 4;
+                const int64_t m = m0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < p.n && k < K) {
+                    if (k < p.k1) {
+                        v = __ldg(reinterpret_cast<const float4*>(p.a1 + m * p.k1 + k));
+                    } else if (!pooled) {
+                        v = __ldg(reinterpret_cast<const float4*>(p.a2 + m * p.k2 + (k - p.k1)));
+                    } else {
+                        const int nv = s_nv[r], kk = k - p.k1;
+#pragma unroll 4
+                        for (int j = 0; j < nv; ++j) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(
+                                p.pool_x + (int64_t)s_id[r * T + j] * p.k2 + kk));
+                            const float wgt = s_w[r * T + j];
+                            v.x = fmaf(wgt, t.x, v.x); v.y = fmaf(wgt, t.y, v.y);
+                            v.z = fmaf(wgt, t.z, v.z); v.w = fmaf(wgt, t.w, v.w);
+                        }
+                    }
+                }
+                av[i] = v;
+            }
+            const int b_iters = (g.umma_n * 8 + kProducers - 1) / kProducers;   // <= 4
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < b_iters) {
+                    const int idx = tid + kProducers * i;
+                    const int nrow = idx >> 3, k = k0 + (idx & 7) * 4;
+                    if (nrow < p.n_out && k < K)
+                        bv[i] = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)nrow * K + k));
+                }
+            }
+            // ---- wait until the MMAs that read this stage last time have completed ----
+            if (u > 0) mbar_wait(bars + 8 * (4 + s), (uint32_t)((u - 1) & 1));
+            // ---- swizzled stores: 16 B chunk j of row r lives at chunk (j ^ (r & 7)) ----
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + kProducers * i;
+                const int r = idx >> 3, j = idx & 7;
+                const uint32_t addr = a_s + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+                st_shared_v4(addr, to_tf32(av[i].x), to_tf32(av[i].y), to_tf32(av[i].z), to_tf32(av[i].w));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < b_iters) {
+                    const int idx = tid + kProducers * i;
+                    const int r = idx >> 3, j = idx & 7;
+                    if (r < g.umma_n) {
+                        const uint32_t addr = b_s + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+                        st_shared_v4(addr, to_tf32(bv[i].x), to_tf32(bv[i].y), to_tf32(bv[i].z), to_tf32(bv[i].w));
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+            mbar_arrive(bars + 8 * s);
+        }
+    } else {
+        // ===================== MMA issuer (one elected lane) =====================
+        // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.umma_n >> 3) << 17) |
+                               ((uint32_t)(kTileM >> 4) << 24);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % g.stages, u = c / g.stages;
+            mbar_wait(bars + 8 * s, (uint32_t)(u & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
+                const uint32_t b_s = a_s + kABytes;
+#pragma unroll
+                for (int k = 0; k < kChunkK / 8; ++k)   // 4 MMAs of K = 8 (32 bytes) per chunk
+                    mma_tf32(tmem_base, make_desc(a_s + k * 32), make_desc(b_s + k * 32), idesc,
+                             (uint32_t)((c | k) != 0));
+                mma_commit(bars + 8 * (4 + s));          // frees the stage when the MMAs finish
+                if (c == nchunks - 1) mma_commit(bars + 64);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ===================== epilogue (warps 0..3: TMEM lane = output row) =====================
+    if (warp < 4) {
+        mbar_wait(bars + 64, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = warp * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const bool relu = p.flags & PB200_EPI_RELU;
+        const bool l2 = p.flags & PB200_EPI_L2NORM;
+        const int ncc = (g.umma_n + 31) / 32;            // 32-column chunks
+        float scale = 1.f;
+        uint32_t v[32];
+        if (l2) {
+            float ss = 0.f;
+            for (int cc = 0; cc < ncc; ++cc) {
+                tmem_ld32(taddr + cc * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = cc * 32 + i;
+                    float f = __uint_as_float(v[i]) + s_bias[col & 255];
+                    if (relu) f = fmaxf(f, 0.f);
+                    if (col < p.n_out) ss = fmaf(f, f, ss);
+                }
+            }
+            scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);      // F.normalize eps
+        }
+        // staging tile per warp: [32 rows][33] floats in the (now idle) stage buffers
+        float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+        for (int cc = 0; cc < ncc; ++cc) {
+            tmem_ld32(taddr + cc * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float f = __uint_as_float(v[i]) + s_bias[(cc * 32 + i) & 255];
+                if (relu) f = fmaxf(f, 0.f);
+                stg[lane * 33 + i] = f * scale;
+            }
+            __syncwarp();
+            const int col = cc * 32 + lane;
+            for (int rr = 0; rr < 32; ++rr) {
+                const int64_t m = m0 + warp * 32 + rr;
+                if (m < p.n && col < p.n_out) p.out[m * p.n_out + col] = stg[rr * 33 + lane];
+            }
+            __syncwarp();
+        }
+        (void)row;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace tc
+
+bool gather_dense_tf32_supported(const DenseParams& p) {
+    const bool pooled = p.pool_x != nullptr && p.k2 > 0;
+    if (p.n_out > 256 || (p.flags & PB200_EPI_LAYERNORM)) return false;
+    if (p.k1 % 4 || p.k2 % 4) return false;
+    if (((uintptr_t)p.a1 | (uintptr_t)p.a2 | (uintptr_t)p.pool_x | (uintptr_t)p.w) % 16) return false;
+    return tc::geometry(p.n_out, p.lists.T, pooled).stages >= 2;
+}
+
+int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {
+    if (!gather_dense_tf32_supported(p)) {
+        set_error("gather_dense: PB200_PREC_TF32 needs n_out <= 256, k1 %% 4 == k2 %% 4 == 0, 16 B "
+                  "aligned operands, no LayerNorm epilogue (got n_out=%d k1=%d k2=%d)", p.n_out,
+                  p.k1, p.k2);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    const bool pooled = p.pool_x != nullptr && p.k2 > 0;
+    const tc::TcGeom g = tc::geometry(p.n_out, p.lists.T, pooled);
+    PB_CUDA(cudaFuncSetAttribute(tc::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)g.smem_bytes));
+    tc::dense_tc_kernel<<<(unsigned)ceil_div(p.n, tc::kTileM), tc::kThreads, g.smem_bytes, stream>>>(p, g);
+    return check_launch("dense_tc_kernel");
+}
+
 }  // namespace pb200

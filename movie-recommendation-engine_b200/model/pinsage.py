@@ -71,7 +71,9 @@ class PinSage(nn.Module):
         self.importance_pooling = ImportancePooling()
         self.output_proj = nn.Linear(hidden_channels, out_channels)
         self.fold = True                 # fold lin_self into lin_update (one GEMM per layer)
-        self.precision = N.PREC_FP32     # PREC_TF32 selects the tcgen05 path
+        # PREC_AUTO: tcgen05 kind::tf32 tensor cores (fp32 accumulate) where the layer shape is
+        # covered, CUDA-core fp32 otherwise; PREC_FP32 forces the exact-fp32 kernels.
+        self.precision = N.PREC_AUTO
         self._folded = {}
 
     # ---- weight preparation (once per parameter version) ---------------------------------

@@ -78,9 +78,12 @@ def _load_model(g, dev):
     return model.to(dev).eval(), layers
 
 
-def test_forward_vs_reference_golden(dev):
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_forward_vs_reference_golden(dev, precision):
+    from mre_b200 import _native as N
     g = Hh.load("forward.npz")
     model, layers = _load_model(g, dev)
+    model.precision = N.PRECISIONS[precision]
     x = torch.from_numpy(g["x"]).to(dev)
     assert Hh.rel_row_err(model(x).cpu().numpy(), g["emb_mlp"]) < TOL                 # MLP branch
     nb0, wt0, nb1, wt1 = Hh.lists_from_json(g, "nb0", "wt0", "nb1", "wt1")
@@ -128,13 +131,17 @@ def test_graph_conv_layer_vs_reference_golden(dev):
         layer.train()(gx, gn)
 
 
-@pytest.mark.parametrize("F_,Hd,E_,T", [(64, 64, 64, 10), (128, 256, 128, 10), (20, 100, 36, 7), (8, 300, 5, 3)])
-def test_forward_dims_vs_oracle(dev, F_, Hd, E_, T):
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+@pytest.mark.parametrize("F_,Hd,E_,T", [(64, 64, 64, 10), (128, 256, 128, 10), (20, 100, 36, 7), (8, 300, 5, 3),
+                                         (30, 50, 7, 40)])
+def test_forward_dims_vs_oracle(dev, F_, Hd, E_, T, precision):
     """C1 / C2 layer widths plus odd sizes (non multiples of 4, > 256 columns)."""
     from mre_b200.model.pinsage import PinSage
+    from mre_b200 import _native as N
     torch.manual_seed(F_ + Hd)
     M = 333
     model = PinSage(F_, Hd, E_, 2).to(dev).eval()
+    model.precision = N.PRECISIONS[precision]
     x = torch.randn(M, F_)
     rng = np.random.Generator(np.random.PCG64(1))
     nbrs = [[rng.integers(0, M + 50, size=int(rng.integers(0, T + 1))).tolist() for _ in range(M)] for _ in range(2)]
@@ -144,3 +151,31 @@ def test_forward_dims_vs_oracle(dev, F_, Hd, E_, T):
     got = model(x.to(dev), None, nbrs, wts).cpu().numpy()
     assert Hh.rel_row_err(got, ref) < TOL
     np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,k1,k2,nout,pooled,flags", [
+    (128, 32, 0, 16, False, 0), (300, 128, 0, 256, False, 1), (1000, 256, 256, 256, True, 3),
+    (777, 256, 0, 128, False, 2), (200, 64, 64, 64, True, 3), (515, 20, 12, 40, False, 1),
+    (1, 8, 0, 8, False, 3), (129, 4, 4, 250, True, 0), (4000, 512, 0, 256, False, 3)])
+def test_tcgen05_dense_vs_cuda_core_fp32(dev, n, k1, k2, nout, pooled, flags):
+    """The tcgen05 kind::tf32 kernel against the exact-fp32 CUDA-core kernel of the same op:
+    TF32 operand rounding only (<= 1e-3 row-relative, the fp32 bar of the north star)."""
+    from mre_b200 import kernels as K, _native as N
+    g = torch.Generator(device="cpu").manual_seed(n + k1 + nout)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)
+    a1, w, b = rnd(n, k1), rnd(nout, k1 + k2) / (k1 + k2) ** 0.5, rnd(nout)
+    kw = {}
+    if k2 and pooled:
+        T = 10
+        ids = torch.randint(0, n + 50, (n, T), generator=g, dtype=torch.int32).to(dev)
+        kw = dict(pool_x=rnd(n, k2), lists=(ids, torch.rand(n, T, generator=g).to(dev),
+                                            torch.randint(0, T + 1, (n,), generator=g, dtype=torch.int32).to(dev), None))
+    elif k2:
+        kw = dict(a2=rnd(n, k2))
+    ref = K.gather_dense(a1, w, b, flags=flags, precision=N.PREC_FP32, **kw).cpu().numpy()
+    got = K.gather_dense(a1, w, b, flags=flags, precision=N.PREC_TF32, **kw).cpu().numpy()
+    assert Hh.rel_row_err(got, ref) < 1e-3
+    # shapes the tensor-core path does not cover are refused loudly, and AUTO routes around them
+    with pytest.raises(N.NativeError, match="PB200_PREC_TF32"):
+        K.gather_dense(rnd(8, 6), rnd(300, 6), None, precision=N.PREC_TF32)
+    assert K.gather_dense(rnd(8, 6), rnd(300, 6), None, precision=N.PREC_AUTO).shape == (8, 300)
