@@ -5,11 +5,12 @@
 //   * lane l runs walks l, l+32, ...; every step draws one 53-bit uniform from
 //     Philox4x32-10 (counter = (start, walk, step/2, epoch)) and picks the first edge whose
 //     row-local cumulative weight exceeds u*total (integer-exact on quantised weights);
-//   * visits go into a per-warp shared-memory hash table (key, count, first-visit index);
+//   * visits go into a per-start shared-memory hash table (key, count | first-visit index);
 //   * the warp selects the top-T by (count desc, first visit asc) -- the reference's
 //     Counter + stable sorted() order (random_walk.py:101-107) -- and emits
 //     weight = count / sum(kept counts) (random_walk.py:113-115).
 // Bound by HBM latency/bandwidth: per step ~ (row_ptr pair + log2(deg) prefix probes + col).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -18,6 +19,9 @@
 namespace pb200 {
 
 constexpr int kEmpty = -1;
+#ifndef PB200_WALK_DEFAULT_VARIANT
+#define PB200_WALK_DEFAULT_VARIANT 102   /* binary search + register select + 6 blocks/SM */
+#endif
 
 struct WalkParams {
     const int64_t* __restrict__ row_ptr;
@@ -40,18 +44,21 @@ struct WalkParams {
     int32_t* __restrict__ trace_out;
 };
 
-__device__ __forceinline__ void table_insert(int32_t* keys, uint32_t* cnt, uint32_t* first,
-                                             int slots, int shift, int node, uint32_t fs) {
+// Per-start hash table: keys[slots] (node id, -1 = empty), cnt[slots], first[slots].  Plain
+// hardware atomics: many lanes of a warp hit the same popular node in the same instruction,
+// which atomicAdd/atomicMin resolve in the LSU (a CAS loop on a packed word serialises).
+__device__ __forceinline__ void table_insert(int32_t* keys, int slots, int shift, int node,
+                                             uint32_t fs) {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + slots);
+    uint32_t* first = cnt + slots;
     uint32_t h = ((uint32_t)node * 2654435761u) >> shift;
     for (;;) {
         const int prev = atomicCAS(&keys[h], kEmpty, node);
-        if (prev == kEmpty || prev == node) {
-            atomicAdd(&cnt[h], 1u);
-            atomicMin(&first[h], fs);
-            return;
-        }
+        if (prev == kEmpty || prev == node) break;
         h = (h + 1) & (uint32_t)(slots - 1);
     }
+    atomicAdd(&cnt[h], 1u);
+    atomicMin(&first[h], fs);
 }
 
 // first p in [r0, r1) with cum[p] > u * total
@@ -99,17 +106,28 @@ __device__ __forceinline__ U8 ld256_stream(const uint32_t* p) { // leaves: strea
                    "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
     return r;
 }
+// number of keys <= t in a sorted node.  The searched node always holds a key > t, so the
+// answer is in [0, 7]: kBin uses three dependent compares, otherwise eight independent ones.
+template <bool kBin>
 __device__ __forceinline__ uint32_t count_le(const U8& k, uint32_t t) {
+    if (kBin) {
+        const bool m1 = k.v[3] <= t;
+        const uint32_t p2 = m1 ? k.v[5] : k.v[1];
+        const bool m2 = p2 <= t;
+        const uint32_t lo = m2 ? k.v[2] : k.v[0], hi = m2 ? k.v[6] : k.v[4];
+        const bool m3 = (m1 ? hi : lo) <= t;
+        return (m1 ? 4u : 0u) + (m2 ? 2u : 0u) + (m3 ? 1u : 0u);
+    }
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) c += (k.v[i] <= t);
     return c;
 }
 
-constexpr int kMaxUpper = 7;   // degree < 8^8
 
 // Returns the next node (>= 0) or -1 at a dead end.  Same rule as pick_edge: first edge whose
 // cumulative weight exceeds t = floor(k53 * total / 2^53).
+template <bool kBin>
 __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
                                             const uint32_t* __restrict__ idx,
                                             const uint32_t* __restrict__ leaf, int cur,
@@ -119,27 +137,24 @@ __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
     const uint64_t total = m.z;
     const uint64_t t64 = (__umul64hi(k53, total) << 11) | ((k53 * total) >> 53);
     const uint32_t t = (uint32_t)t64;
-    uint32_t nbl[kMaxUpper + 1];
-    nbl[0] = (m.y + 7u) >> 3;
-    int L = 0;
-#pragma unroll
-    for (int l = 1; l <= kMaxUpper; ++l) {
-        nbl[l] = (nbl[l - 1] + 7u) >> 3;
-        L += (nbl[l - 1] > 1u);
-    }
-    uint32_t pos = 0, off = m.w;
-#pragma unroll
-    for (int l = kMaxUpper; l >= 1; --l) {
-        if (l <= L) {
+    // upper levels: L = ceil(log8(leaf blocks)); level l holds ceil(nb0 / 8^l) blocks, stored
+    // top level first.  A real loop (the trip count is 1-2 for typical degrees).
+    const uint32_t nb0 = (m.y + 7u) >> 3;
+    uint32_t pos = 0;
+    if (nb0 > 1u) {
+        int l = (((31 - __clz(nb0 - 1u)) * 11) >> 5) + 1;      // floor(log2(nb0-1)) / 3 + 1
+        uint32_t off = m.w;
+#pragma unroll 1
+        for (; l >= 1; --l) {
             const U8 k = ld256_keep(idx + ((size_t)(off + pos) << 3));
-            pos = pos * 8u + count_le(k, t);
-            off += nbl[l];
+            pos = pos * 8u + count_le<kBin>(k, t);
+            off += (nb0 + (1u << (3 * l)) - 1u) >> (3 * l);
         }
     }
     const uint32_t* blk = leaf + ((size_t)(m.x + pos) << 4);
     const U8 keys = ld256_stream(blk);
     const U8 cols = ld256_stream(blk + 8);
-    const uint32_t c = count_le(keys, t);
+    const uint32_t c = count_le<kBin>(keys, t);
     uint32_t next = cols.v[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i) next = (c == (uint32_t)i) ? cols.v[i] : next;
@@ -148,23 +163,40 @@ __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
 
 enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3 };
 
-template <int kMode>
-__global__ void __launch_bounds__(256) walk_topt_kernel(const WalkParams p) {
+// 8 sorted values per lane (descending) -- Batcher odd-even merge sort network, 19 exchanges
+__device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {   // a >= b afterwards
+    const uint32_t hi = max(a, b), lo = min(a, b);
+    a = hi; b = lo;
+}
+__device__ __forceinline__ void sort8_desc(uint32_t (&v)[8]) {
+    cex(v[0], v[1]); cex(v[2], v[3]); cex(v[4], v[5]); cex(v[6], v[7]);
+    cex(v[0], v[2]); cex(v[1], v[3]); cex(v[4], v[6]); cex(v[5], v[7]);
+    cex(v[1], v[2]); cex(v[5], v[6]);
+    cex(v[0], v[4]); cex(v[1], v[5]); cex(v[2], v[6]); cex(v[3], v[7]);
+    cex(v[2], v[4]); cex(v[3], v[5]);
+    cex(v[1], v[2]); cex(v[3], v[4]); cex(v[5], v[6]);
+}
+
+// Warp-level structure: one warp per start node (warps never wait for each other).  Lane l
+// runs walks l, l+32, ...: the start node, its table and its row are warp-uniform, so the
+// first step's loads are broadcasts.  (Measured alternatives, tools/tune_walk.py: two starts
+// per warp and block-wide flattening of the (start, walk) pairs are both slower.)
+template <int kMode, bool kBin, bool kRegSel, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkParams p) {
     constexpr bool kCountOnly = kMode == kCountTrace;
     using CumT = typename std::conditional<kMode == kFlatF64, double, uint32_t>::type;
     extern __shared__ int32_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int warps_per_block = blockDim.x >> 5;
-    int32_t* keys = smem + (size_t)warp * 3 * p.slots;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + p.slots);
-    uint32_t* first = cnt + p.slots;
+    const int kWarpsPerBlock = blockDim.x >> 5;
     const int V = p.W * p.L;
+    int32_t* keys = smem + (size_t)warp * 3 * p.slots;   // [keys | cnt | first]
+    const CumT* __restrict__ cum = static_cast<const CumT*>(p.cum);
 
-    for (int64_t s = (int64_t)blockIdx.x * warps_per_block + warp; s < p.n;
-         s += (int64_t)gridDim.x * warps_per_block) {
+    for (int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp; s < p.n;
+         s += (int64_t)gridDim.x * kWarpsPerBlock) {
         for (int i = lane; i < p.slots; i += 32) {
-            keys[i] = kEmpty; cnt[i] = 0u; first[i] = 0xFFFFFFFFu;
+            keys[i] = kEmpty; keys[p.slots + i] = 0; keys[2 * p.slots + i] = -1;
         }
         __syncwarp();
 
@@ -172,93 +204,130 @@ __global__ void __launch_bounds__(256) walk_topt_kernel(const WalkParams p) {
             const int32_t* tr = p.trace_in + s * V;
             for (int i = lane; i < V; i += 32) {
                 const int v = tr[i];
-                if (v >= 0) table_insert(keys, cnt, first, p.slots, p.slot_shift, v, (uint32_t)i);
+                if (v >= 0) table_insert(keys, p.slots, p.slot_shift, v, (uint32_t)i);
             }
         } else {
-            const CumT* __restrict__ cum = static_cast<const CumT*>(p.cum);
             const int start = p.starts[s];
-            int32_t* tr = p.trace_out ? p.trace_out + s * V : nullptr;
-            for (int wbase = 0; wbase < p.W; wbase += 32) {
-                const int walk = wbase + lane;
-                bool active = walk < p.W;
+            for (int walk = lane; walk < p.W; walk += 32) {
+                int32_t* tr = p.trace_out ? p.trace_out + (s * p.W + walk) * p.L : nullptr;
                 int cur = start;
                 Philox4 r;
-                for (int l = 0; l < p.L; ++l) {
-                    if (active && (l & 1) == 0)
+                int l = 0;
+                for (; l < p.L; ++l) {
+                    if ((l & 1) == 0)
                         r = philox4x32_10((uint32_t)start, (uint32_t)walk, (uint32_t)(l >> 1),
                                           p.epoch, p.seed_lo, p.seed_hi);
+                    const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
+                                                 : uniform53(r.v[0], r.v[1]);
                     int next = -1;
-                    if (active) {
-                        const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
-                                                     : uniform53(r.v[0], r.v[1]);
-                        if (kMode == kIndexed) {
-                            next = indexed_step(p.meta, p.idx, p.leaf, cur, k53);
-                        } else {
-                            const int64_t r0 = __ldg(p.row_ptr + cur);
-                            const int64_t r1 = __ldg(p.row_ptr + cur + 1);
-                            if (r1 != r0) next = __ldg(p.col + pick_edge(cum, r0, r1, k53));
-                        }
-                        if (next < 0) {
-                            active = false;  // dead end: random_walk.py:68-69
-                        } else {
-                            cur = next;
-                            table_insert(keys, cnt, first, p.slots, p.slot_shift, next,
-                                         (uint32_t)(walk * p.L + l));
-                        }
+                    if (kMode == kIndexed) {
+                        next = indexed_step<kBin>(p.meta, p.idx, p.leaf, cur, k53);
+                    } else {
+                        const int64_t r0 = __ldg(p.row_ptr + cur);
+                        const int64_t r1 = __ldg(p.row_ptr + cur + 1);
+                        if (r1 != r0) next = __ldg(p.col + pick_edge(cum, r0, r1, k53));
                     }
-                    if (tr && walk < p.W) tr[walk * p.L + l] = next;
+                    if (next < 0) break;   // dead end: random_walk.py:68-69
+                    cur = next;
+                    table_insert(keys, p.slots, p.slot_shift, next, (uint32_t)(walk * p.L + l));
+                    if (tr) tr[l] = next;
                 }
+                if (tr) for (; l < p.L; ++l) tr[l] = -1;
             }
         }
         __syncwarp();
 
-        // sort key: count in the high half, (0xFFFF - first visit) in the low half; unique
-        // per node because first-visit indices are unique.
-        for (int i = lane; i < p.slots; i += 32) {
-            const uint32_t c = cnt[i];
-            cnt[i] = c ? ((c << 16) | (0xFFFFu - first[i])) : 0u;
-        }
-        // slot i is only ever touched by lane (i & 31) from here on: no sync needed
-        int32_t* o_ids = p.out_ids + s * p.T;
-        int32_t* o_cnt = p.out_counts + s * p.T;
-        float* o_w = p.out_w + s * p.T;
-        uint32_t total = 0;
-        int nvalid = 0;
-        for (int j = 0; j < p.T; ++j) {
-            uint32_t best = 0;
-            int bslot = -1;
-            for (int i = lane; i < p.slots; i += 32) {
-                const uint32_t v = cnt[i];
-                if (v > best) { best = v; bslot = i; }
-            }
-            const uint32_t m = __reduce_max_sync(kFull, best);
-            if (m == 0) break;  // fewer than T distinct nodes (warp-uniform)
-            const int src = __ffs(__ballot_sync(kFull, best == m)) - 1;
-            int node = 0;
-            if (lane == src) { node = keys[bslot]; cnt[bslot] = 0u; }
-            node = __shfl_sync(kFull, node, src);
-            const uint32_t c = m >> 16;
-            total += c;
-            if (lane == (j & 31)) { o_ids[j] = node; o_cnt[j] = (int32_t)c; }
-            ++nvalid;
-        }
-        // weights (float64 division like the reference, then the fp32 cast that
-        // torch.tensor(list) applies in ImportancePooling, model/pinsage.py:140)
-        for (int j = lane; j < p.T; j += 32) {
-            if (j < nvalid) {
-                o_w[j] = (float)((double)o_cnt[j] / (double)total);  // own earlier store
+        // ---- top-T by (count desc, first visit asc) ----
+        {
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + p.slots);
+            uint32_t* first = cnt + p.slots;
+            int32_t* o_ids = p.out_ids + s * p.T;
+            int32_t* o_cnt = p.out_counts + s * p.T;
+            float* o_w = p.out_w + s * p.T;
+            uint32_t total = 0;
+            int nvalid = 0;
+            if (kRegSel && p.slots == 256 && V <= 255) {
+                // fast path: key = count<<16 | (255-first)<<8 | slot; 8 keys per lane, sorted
+                // once in registers; every round pops the warp-wide maximum.
+                uint32_t k[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int slot = i * 32 + lane;
+                    const uint32_t c = cnt[slot];
+                    k[i] = c ? ((c << 16) | ((255u - first[slot]) << 8) | (uint32_t)slot) : 0u;
+                }
+                sort8_desc(k);
+                for (int j = 0; j < p.T; ++j) {
+                    const uint32_t m = __reduce_max_sync(kFull, k[0]);
+                    if (m == 0) break;                     // fewer than T distinct nodes
+                    if (k[0] == m) {                       // unique winner pops its head
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) k[i] = k[i + 1];
+                        k[7] = 0u;
+                    }
+                    const uint32_t c = m >> 16;
+                    total += c;
+                    if (lane == (j & 31)) { o_ids[j] = keys[m & 255u]; o_cnt[j] = (int32_t)c; }
+                    ++nvalid;
+                }
             } else {
-                o_ids[j] = -1; o_cnt[j] = 0; o_w[j] = 0.0f;
+                // generic path: sort key = count<<16 | (0xFFFF - first), unique per node (first
+                // visit indices are unique); T rounds of arg-max; a slot is only touched by lane
+                // (slot & 31) from here on
+                for (int i = lane; i < p.slots; i += 32) {
+                    const uint32_t c = cnt[i];
+                    cnt[i] = c ? ((c << 16) | (0xFFFFu - first[i])) : 0u;
+                }
+                for (int j = 0; j < p.T; ++j) {
+                    uint32_t best = 0;
+                    int bslot = -1;
+                    for (int i = lane; i < p.slots; i += 32) {
+                        const uint32_t v = cnt[i];
+                        if (v > best) { best = v; bslot = i; }
+                    }
+                    const uint32_t m = __reduce_max_sync(kFull, best);
+                    if (m == 0) break;
+                    const int src = __ffs(__ballot_sync(kFull, best == m)) - 1;
+                    int node = 0;
+                    if (lane == src) { node = keys[bslot]; cnt[bslot] = 0u; }
+                    node = __shfl_sync(kFull, node, src);
+                    const uint32_t c = m >> 16;
+                    total += c;
+                    if (lane == (j & 31)) { o_ids[j] = node; o_cnt[j] = (int32_t)c; }
+                    ++nvalid;
+                }
             }
+            // weights: float64 division like the reference, then the fp32 cast that
+            // torch.tensor(list) applies in ImportancePooling (model/pinsage.py:140)
+            for (int j = lane; j < p.T; j += 32) {
+                if (j < nvalid) {
+                    o_w[j] = (float)((double)o_cnt[j] / (double)total);  // own earlier store
+                } else {
+                    o_ids[j] = -1; o_cnt[j] = 0; o_w[j] = 0.0f;
+                }
+            }
+            if (lane == 0) p.out_nvalid[s] = nvalid;
         }
-        if (lane == 0) p.out_nvalid[s] = nvalid;
         __syncwarp();
     }
 }
 
+template <int kMode, bool kBin, bool kRegSel, int kMinBlocks>
+static int launch_variant(const WalkParams& p, int warps, size_t smem, cudaStream_t stream) {
+    auto kern = walk_topt_kernel<kMode, kBin, kRegSel, kMinBlocks>;
+    if (smem > 48 * 1024)
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // enough blocks to fill every SM several times; grid-stride over the rest
+    int64_t blocks = ceil_div(p.n, (int64_t)warps);
+    const int64_t cap = (int64_t)kSMs * 32;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
+    return check_launch("walk_topt_kernel");
+}
+
 static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_t stream) {
     const int V = p.W * p.L;
-    int slots = 64;
+    int slots = 256;
     while (slots < V + V / 4 + 1) slots <<= 1;
     p.slots = slots;
     int lg = 0;
@@ -273,17 +342,24 @@ static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_
         return PB200_ERR_UNSUPPORTED;
     }
     const size_t smem = per_warp * warps;
-    auto kern = count_only ? walk_topt_kernel<kCountTrace>
-              : p.meta ? walk_topt_kernel<kIndexed>
-              : cum_kind == 0 ? walk_topt_kernel<kFlatU32> : walk_topt_kernel<kFlatF64>;
-    if (smem > 48 * 1024)
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // enough blocks to fill every SM several times; grid-stride over the rest
-    int64_t blocks = ceil_div(p.n, warps);
-    const int64_t cap = (int64_t)kSMs * 32;
-    if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(p);
-    return check_launch("walk_topt_kernel");
+    if (count_only) return launch_variant<kCountTrace, false, true, 1>(p, warps, smem, stream);
+    if (!p.meta)
+        return cum_kind == 0 ? launch_variant<kFlatU32, false, true, 1>(p, warps, smem, stream)
+                             : launch_variant<kFlatF64, false, true, 1>(p, warps, smem, stream);
+    // tuning knob (tools/tune_walk.py): bit1 = binary in-node search, bit2 = register top-T
+    // selection, bits 4.. = min resident blocks per SM (register cap); unset = tuned default
+    static const int variant = [] { const char* e = getenv("PB200_WALK_VARIANT"); return e ? atoi(e) : -1; }();
+    const int v = variant >= 0 ? variant : PB200_WALK_DEFAULT_VARIANT;
+    const bool bin = v & 2, reg = v & 4;
+    const int minb = v >> 4;
+#define PB_V(B_, R_, M_) return launch_variant<kIndexed, B_, R_, M_>(p, warps, smem, stream)
+#define PB_VM(B_, R_) do { if (minb == 5) PB_V(B_, R_, 5); if (minb == 6) PB_V(B_, R_, 6); \
+                           if (minb == 7) PB_V(B_, R_, 7); PB_V(B_, R_, 1); } while (0)
+    if (bin) { if (reg) PB_VM(true, true); PB_VM(true, false); }
+    if (reg) PB_VM(false, true);
+    PB_VM(false, false);
+#undef PB_VM
+#undef PB_V
 }
 
 }  // namespace pb200
