@@ -110,13 +110,13 @@ __host__ __device__ inline TcGeom geometry(int n_out, int T, bool pooled) {
     g.b_bytes = g.umma_n * 128;
     g.stage_bytes = kABytes + g.b_bytes;                        // multiples of 1024
     const size_t lists = pooled ? (size_t)kTileM * (4 + (size_t)T * 8) : 0;
-    const size_t fixed = 1024 /*alignment slack*/ + lists + 256 * 4 /*bias*/ + 256 /*barriers*/;
+    const size_t fixed = 1024 /*alignment slack*/ + lists + 256 * 4 /*bias*/ + 1024 /*barriers + row scales*/;
     int s = (int)((220 * 1024 - fixed) / g.stage_bytes);
     g.stages = s > 4 ? 4 : s;
     g.off_lists = (size_t)g.stages * g.stage_bytes;
     g.off_bias = g.off_lists + lists;
     g.off_bars = g.off_bias + 256 * 4;
-    g.smem_bytes = g.off_bars + 256 + 1024;
+    g.smem_bytes = g.off_bars + 1024 + 1024;
     return g;
 }
 
@@ -168,31 +168,55 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
 
     if (warp < kProducerWarps) {
         // ===================== producers =====================
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % g.stages, u = c / g.stages;
-            const int k0 = c * kChunkK;
-            const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
-            const uint32_t b_s = a_s + kABytes;
-            // ---- issue the global loads of this chunk first (A: 2, B: up to 4 float4) ----
-            float4 av[2], bv[4];
+        // Per-thread constants: which (row, 16 B chunk) pairs of the A tile (2) and of the W tile
+        // (<= 4) this thread moves every K chunk, their global row pointers and their swizzled
+        // shared-memory offsets (16 B chunk j of row r lives at chunk j ^ (r & 7)).
+        const int j = tid & 7;                          // 16-byte chunk inside the 128 B row
+        const int b_iters = (g.umma_n * 8 + kProducers - 1) / kProducers;   // <= 4
+        int a_row[2]; uint32_t a_off[2]; bool a_ok[2];
+        const float* a1p[2]; const float* a2p[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = (tid + kProducers * i) >> 3;
+            const int64_t m = m0 + r;
+            a_row[i] = r;
+            a_ok[i] = m < p.n;
+            a_off[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+            a1p[i] = p.a1 + (a_ok[i] ? m : 0) * p.k1 + j * 4;
+            a2p[i] = (pooled || !p.a2) ? nullptr : p.a2 + (a_ok[i] ? m : 0) * p.k2 + j * 4;
+        }
+        uint32_t b_off[4]; bool b_ok[4]; const float* bp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = (tid + kProducers * i) >> 3;
+            b_ok[i] = i < b_iters && r < p.n_out;
+            b_off[i] = (uint32_t)(kABytes + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+            bp[i] = p.w + (int64_t)(b_ok[i] ? r : 0) * K + j * 4;
+        }
+        const bool b_store3 = 3 < b_iters && ((tid + kProducers * 3) >> 3) < g.umma_n;
+        const bool b_store2 = 2 < b_iters && ((tid + kProducers * 2) >> 3) < g.umma_n;
+        const bool b_store1 = 1 < b_iters && ((tid + kProducers * 1) >> 3) < g.umma_n;
+        const bool b_store0 = ((tid) >> 3) < g.umma_n;
+
+        auto load_chunk = [&](int c, float4 (&av)[2], float4 (&bv)[4]) {
+            const int k = c * kChunkK + j * 4;          // first column of this thread's 16 B
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int idx = tid + kProducers * i;
-                const int r = idx >> 3, k = k0 + (idx & 7) * 4;
-                const int64_t m = m0 + r;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < p.n && k < K) {
+                if (a_ok[i] && k < K) {
                     if (k < p.k1) {
-                        v = __ldg(reinterpret_cast<const float4*>(p.a1 + m * p.k1 + k));
+                        v = __ldg(reinterpret_cast<const float4*>(a1p[i] + c * kChunkK));
                     } else if (!pooled) {
-                        v = __ldg(reinterpret_cast<const float4*>(p.a2 + m * p.k2 + (k - p.k1)));
+                        v = __ldg(reinterpret_cast<const float4*>(a2p[i] + (c * kChunkK - p.k1)));
                     } else {
-                        const int nv = s_nv[r], kk = k - p.k1;
-#pragma unroll 4
-                        for (int j = 0; j < nv; ++j) {
+                        const int r = a_row[i], nv = s_nv[r], kk = k - p.k1;
+                        const int* ids = s_id + r * T;
+                        const float* ws = s_w + r * T;
+#pragma unroll 2
+                        for (int q = 0; q < nv; ++q) {
                             const float4 t = __ldg(reinterpret_cast<const float4*>(
-                                p.pool_x + (int64_t)s_id[r * T + j] * p.k2 + kk));
-                            const float wgt = s_w[r * T + j];
+                                p.pool_x + (int64_t)ids[q] * p.k2 + kk));
+                            const float wgt = ws[q];
                             v.x = fmaf(wgt, t.x, v.x); v.y = fmaf(wgt, t.y, v.y);
                             v.z = fmaf(wgt, t.z, v.z); v.w = fmaf(wgt, t.w, v.w);
                         }
@@ -200,40 +224,34 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 }
                 av[i] = v;
             }
-            const int b_iters = (g.umma_n * 8 + kProducers - 1) / kProducers;   // <= 4
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < b_iters) {
-                    const int idx = tid + kProducers * i;
-                    const int nrow = idx >> 3, k = k0 + (idx & 7) * 4;
-                    if (nrow < p.n_out && k < K)
-                        bv[i] = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)nrow * K + k));
-                }
+                if (b_ok[i] && k < K) bv[i] = __ldg(reinterpret_cast<const float4*>(bp[i] + c * kChunkK));
             }
-            // ---- wait until the MMAs that read this stage last time have completed ----
+        };
+
+        float4 av[2], bv[4], av_n[2], bv_n[4];
+        load_chunk(0, av, bv);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % g.stages, u = c / g.stages;
+            if (c + 1 < nchunks) load_chunk(c + 1, av_n, bv_n);   // in flight during wait + store
+            // the MMAs that read this stage last time must have completed
             if (u > 0) mbar_wait(bars + 8 * (4 + s), (uint32_t)((u - 1) & 1));
-            // ---- swizzled stores: 16 B chunk j of row r lives at chunk (j ^ (r & 7)) ----
+            const uint32_t st = sbase + (uint32_t)s * g.stage_bytes;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int idx = tid + kProducers * i;
-                const int r = idx >> 3, j = idx & 7;
-                const uint32_t addr = a_s + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-                st_shared_v4(addr, to_tf32(av[i].x), to_tf32(av[i].y), to_tf32(av[i].z), to_tf32(av[i].w));
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < b_iters) {
-                    const int idx = tid + kProducers * i;
-                    const int r = idx >> 3, j = idx & 7;
-                    if (r < g.umma_n) {
-                        const uint32_t addr = b_s + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-                        st_shared_v4(addr, to_tf32(bv[i].x), to_tf32(bv[i].y), to_tf32(bv[i].z), to_tf32(bv[i].w));
-                    }
-                }
-            }
+            for (int i = 0; i < 2; ++i)
+                st_shared_v4(st + a_off[i], to_tf32(av[i].x), to_tf32(av[i].y), to_tf32(av[i].z), to_tf32(av[i].w));
+            if (b_store0) st_shared_v4(st + b_off[0], to_tf32(bv[0].x), to_tf32(bv[0].y), to_tf32(bv[0].z), to_tf32(bv[0].w));
+            if (b_store1) st_shared_v4(st + b_off[1], to_tf32(bv[1].x), to_tf32(bv[1].y), to_tf32(bv[1].z), to_tf32(bv[1].w));
+            if (b_store2) st_shared_v4(st + b_off[2], to_tf32(bv[2].x), to_tf32(bv[2].y), to_tf32(bv[2].z), to_tf32(bv[2].w));
+            if (b_store3) st_shared_v4(st + b_off[3], to_tf32(bv[3].x), to_tf32(bv[3].y), to_tf32(bv[3].z), to_tf32(bv[3].w));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
             mbar_arrive(bars + 8 * s);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) av[i] = av_n[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bv[i] = bv_n[i];
         }
     } else {
         // ===================== MMA issuer (one elected lane) =====================
@@ -258,53 +276,69 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
         }
     }
 
-    // ===================== epilogue (warps 0..3: TMEM lane = output row) =====================
+    // ===================== epilogue =====================
+    // warps 0..3 (TMEM lane = output row): one pass over the accumulator -> bias, ReLU, sum of
+    // squares -> un-normalised row into the staging tile (the idle stage buffers, row stride
+    // N+4 floats: conflict-free 16 B stores); then all 16 producer warps scale and write the
+    // tile with coalesced 16 B stores.
+    float* stg = reinterpret_cast<float*>(smem);
+    float* s_scale = reinterpret_cast<float*>(smem + g.off_bars + 128);   // [128] after the barriers
+    const int ldst = g.umma_n + 4;
     if (warp < 4) {
         mbar_wait(bars + 64, 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = warp * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
         const bool relu = p.flags & PB200_EPI_RELU;
-        const bool l2 = p.flags & PB200_EPI_L2NORM;
-        const int ncc = (g.umma_n + 31) / 32;            // 32-column chunks
-        float scale = 1.f;
+        const int ncc = g.umma_n / 16;                   // 16-column pieces
+        float ss = 0.f;
         uint32_t v[32];
-        if (l2) {
-            float ss = 0.f;
-            for (int cc = 0; cc < ncc; ++cc) {
-                tmem_ld32(taddr + cc * 32, v);
+        for (int cc = 0; cc < ncc; cc += 2) {
+            tmem_ld32(taddr + cc * 16, v);               // 32 columns (reads past umma_n stay inside the allocation)
+            const int ncol = min(32, g.umma_n - cc * 16);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int col = cc * 32 + i;
-                    float f = __uint_as_float(v[i]) + s_bias[col & 255];
-                    if (relu) f = fmaxf(f, 0.f);
-                    if (col < p.n_out) ss = fmaf(f, f, ss);
+            for (int i = 0; i < 32; i += 4) {
+                if (i < ncol) {
+                    float f[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = cc * 16 + i + e;
+                        float x = __uint_as_float(v[i + e]) + s_bias[col & 255];
+                        if (relu) x = fmaxf(x, 0.f);
+                        if (col >= p.n_out) x = 0.f;
+                        ss = fmaf(x, x, ss);
+                        f[e] = x;
+                    }
+                    *reinterpret_cast<float4*>(stg + (size_t)row * ldst + cc * 16 + i) =
+                        make_float4(f[0], f[1], f[2], f[3]);
                 }
             }
-            scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);      // F.normalize eps
         }
-        // staging tile per warp: [32 rows][33] floats in the (now idle) stage buffers
-        float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-        for (int cc = 0; cc < ncc; ++cc) {
-            tmem_ld32(taddr + cc * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float f = __uint_as_float(v[i]) + s_bias[(cc * 32 + i) & 255];
-                if (relu) f = fmaxf(f, 0.f);
-                stg[lane * 33 + i] = f * scale;
-            }
-            __syncwarp();
-            const int col = cc * 32 + lane;
-            for (int rr = 0; rr < 32; ++rr) {
-                const int64_t m = m0 + warp * 32 + rr;
-                if (m < p.n && col < p.n_out) p.out[m * p.n_out + col] = stg[rr * 33 + lane];
-            }
-            __syncwarp();
-        }
-        (void)row;
+        s_scale[row] = (p.flags & PB200_EPI_L2NORM) ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;   // F.normalize eps
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (warp < kProducerWarps) {
+        const bool vec_out = (p.n_out & 3) == 0 && ((uintptr_t)p.out & 15) == 0;
+        const int n4 = (p.n_out + 3) >> 2;               // float4 pieces per row
+        for (int idx = tid; idx < kTileM * n4; idx += kProducers) {
+            const int r = idx / n4, c4 = (idx - r * n4) * 4;
+            const int64_t m = m0 + r;
+            if (m >= p.n) continue;
+            float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * ldst + c4);
+            const float sc = s_scale[r];
+            x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+            float* o = p.out + m * p.n_out + c4;
+            if (vec_out) {
+                *reinterpret_cast<float4*>(o) = x;
+            } else {
+                o[0] = x.x;
+                if (c4 + 1 < p.n_out) o[1] = x.y;
+                if (c4 + 2 < p.n_out) o[2] = x.z;
+                if (c4 + 3 < p.n_out) o[3] = x.w;
+            }
+        }
+    }
     if (warp == kProducerWarps) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -319,7 +353,9 @@ bool gather_dense_tf32_supported(const DenseParams& p) {
     if (p.n_out > 256 || (p.flags & PB200_EPI_LAYERNORM)) return false;
     if (p.k1 % 4 || p.k2 % 4) return false;
     if (((uintptr_t)p.a1 | (uintptr_t)p.a2 | (uintptr_t)p.pool_x | (uintptr_t)p.w) % 16) return false;
-    return tc::geometry(p.n_out, p.lists.T, pooled).stages >= 2;
+    const tc::TcGeom g = tc::geometry(p.n_out, p.lists.T, pooled);
+    // the epilogue stages the whole 128 x (N+4) fp32 tile in the pipeline buffers
+    return g.stages >= 2 && (size_t)g.stages * g.stage_bytes >= (size_t)tc::kTileM * (g.umma_n + 4) * 4;
 }
 
 int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {

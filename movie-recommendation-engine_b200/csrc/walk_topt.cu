@@ -246,30 +246,58 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
             float* o_w = p.out_w + s * p.T;
             uint32_t total = 0;
             int nvalid = 0;
-            if (kRegSel && p.slots == 256 && V <= 255) {
-                // fast path: key = count<<16 | (255-first)<<8 | slot; 8 keys per lane, sorted
-                // once in registers; every round pops the warp-wide maximum.
-                uint32_t k[8];
+            if (kRegSel && p.slots <= 512 && V <= 255 && p.T <= 32) {
+                // fast path: key = count<<16 | (255-first)<<8... packed with the slot index so
+                // that the winner's node id is one broadcast shared-memory load; keys are sorted
+                // once per lane in registers and every round pops the warp-wide maximum.  Lane j
+                // keeps the j-th winner: the results leave the warp as three coalesced stores.
+                uint32_t k[8], k2[8];
+                const bool wide = p.slots == 512;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int slot = i * 32 + lane;
                     const uint32_t c = cnt[slot];
-                    k[i] = c ? ((c << 16) | ((255u - first[slot]) << 8) | (uint32_t)slot) : 0u;
+                    k[i] = c ? ((c << 17) | ((255u - first[slot]) << 9) | (uint32_t)slot) : 0u;
+                    k2[i] = 0u;
+                    if (wide) {
+                        const uint32_t c2 = cnt[slot + 256];
+                        k2[i] = c2 ? ((c2 << 17) | ((255u - first[slot + 256]) << 9) | (uint32_t)(slot + 256)) : 0u;
+                    }
                 }
                 sort8_desc(k);
+                if (wide) sort8_desc(k2);
+                int my_id = -1; uint32_t my_cnt = 0;
                 for (int j = 0; j < p.T; ++j) {
-                    const uint32_t m = __reduce_max_sync(kFull, k[0]);
+                    const uint32_t head = max(k[0], k2[0]);
+                    const uint32_t m = __reduce_max_sync(kFull, head);
                     if (m == 0) break;                     // fewer than T distinct nodes
                     if (k[0] == m) {                       // unique winner pops its head
 #pragma unroll
                         for (int i = 0; i < 7; ++i) k[i] = k[i + 1];
                         k[7] = 0u;
+                    } else if (k2[0] == m) {
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) k2[i] = k2[i + 1];
+                        k2[7] = 0u;
                     }
-                    const uint32_t c = m >> 16;
+                    const uint32_t c = m >> 17;
+                    const int node = keys[m & 511u];       // broadcast
                     total += c;
-                    if (lane == (j & 31)) { o_ids[j] = keys[m & 255u]; o_cnt[j] = (int32_t)c; }
+                    my_id = lane == j ? node : my_id;
+                    my_cnt = lane == j ? c : my_cnt;
                     ++nvalid;
                 }
+                if (lane < p.T) {
+                    const bool has = lane < nvalid;
+                    o_ids[lane] = has ? my_id : -1;
+                    o_cnt[lane] = has ? (int32_t)my_cnt : 0;
+                    // float64 division like the reference, then the fp32 cast that
+                    // torch.tensor(list) applies in ImportancePooling (model/pinsage.py:140)
+                    o_w[lane] = has ? (float)((double)my_cnt / (double)total) : 0.0f;
+                }
+                if (lane == 0) p.out_nvalid[s] = nvalid;
+                __syncwarp();
+                continue;
             } else {
                 // generic path: sort key = count<<16 | (0xFFFF - first), unique per node (first
                 // visit indices are unique); T rounds of arg-max; a slot is only touched by lane
@@ -326,9 +354,15 @@ static int launch_variant(const WalkParams& p, int warps, size_t smem, cudaStrea
 }
 
 static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_t stream) {
+    // tuning knob (tools/tune_walk.py): bit1 = binary in-node search, bit2 = register top-T
+    // selection, bit3 = hash table twice as large, bits 4.. = min resident blocks per SM
+    // (register cap); unset = tuned default
+    static const int variant = [] { const char* e = getenv("PB200_WALK_VARIANT"); return e ? atoi(e) : -1; }();
+    const int v = variant >= 0 ? variant : PB200_WALK_DEFAULT_VARIANT;
     const int V = p.W * p.L;
     int slots = 256;
     while (slots < V + V / 4 + 1) slots <<= 1;
+    if (v & 8) slots <<= 1;
     p.slots = slots;
     int lg = 0;
     while ((1 << lg) < slots) ++lg;
@@ -346,10 +380,6 @@ static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_
     if (!p.meta)
         return cum_kind == 0 ? launch_variant<kFlatU32, false, true, 1>(p, warps, smem, stream)
                              : launch_variant<kFlatF64, false, true, 1>(p, warps, smem, stream);
-    // tuning knob (tools/tune_walk.py): bit1 = binary in-node search, bit2 = register top-T
-    // selection, bits 4.. = min resident blocks per SM (register cap); unset = tuned default
-    static const int variant = [] { const char* e = getenv("PB200_WALK_VARIANT"); return e ? atoi(e) : -1; }();
-    const int v = variant >= 0 ? variant : PB200_WALK_DEFAULT_VARIANT;
     const bool bin = v & 2, reg = v & 4;
     const int minb = v >> 4;
 #define PB_V(B_, R_, M_) return launch_variant<kIndexed, B_, R_, M_>(p, warps, smem, stream)
