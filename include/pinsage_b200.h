@@ -161,6 +161,11 @@ int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
 #define PB200_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM; UNSUPPORTED if the shape is not covered */
 #define PB200_PREC_AUTO 2 /* TF32 tensor cores where the shape is covered, CUDA-core fp32 otherwise */
 
+/* out[i] = in[i] rounded to TF32 (round-to-nearest, ties away: cvt.rna.tf32.f32); in == out ok.
+ * The tensor core reads only the 19 high bits of a TF32 operand, so weights handed to the
+ * PB200_PREC_TF32 / AUTO path should be pre-rounded once (activations are rounded in-kernel). */
+int pb200_round_tf32(const float* in, float* out, int64_t n, pb200_stream_t stream);
+
 int pb200_gather_dense(const float* a1, int k1, const float* a2, int k2, const float* pool_x,
                        int64_t pool_rows, const int32_t* ids, const float* weights,
                        const int32_t* list_len, const int32_t* weight_len, int max_neighbors,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "pb200_gather_dense": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
                                    c_int, c_int, c_ptr, c_ptr]),
+    "pb200_round_tf32": (c_int, [c_ptr, c_ptr, c_i64, c_ptr]),
     "pb200_topk_workspace_bytes": (c_size, [c_i64, c_i64, c_int, c_int]),
     "pb200_topk": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i32, c_ptr,
                            c_ptr, c_ptr, c_size, c_ptr]),

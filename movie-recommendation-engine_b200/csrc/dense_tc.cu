@@ -2,26 +2,32 @@
 //
 //   out[m,:] = epi( [A1[m,:K1] | A2row(m)] . W^T + bias ),  A2row dense or pooled on the fly
 //
-// One CTA per 128-row tile (UMMA M=128, N = n_out rounded up to 16 <= 256, K=8 per MMA):
-//   warps 0..15  producers: build the K-major, 128B-swizzled A tile ([h | sum_j w_j h[id_j]],
-//                16-byte vector loads, rounded to TF32 with cvt.rna) and the W tile in shared
-//                memory, S-stage ring, fence.proxy.async + mbarrier arrive per stage
-//   warp 16      one elected thread issues tcgen05.mma (accumulator in TMEM) and
+// One CTA per 128-row tile (UMMA M=128, N = n_out rounded up to 16 <= 256, K=8 per MMA),
+// 13 warps, S-stage shared-memory ring of K-major 128B-swizzled operand tiles:
+//   warps 0..7   A producers: [h | sum_j w_j h[id_j]] built from 16-byte vector loads (the
+//                neighbour rows), rounded to TF32 (cvt.rna), written with the swizzle applied
+//                by hand; a 3-deep register ring keeps two K chunks of loads in flight
+//   warps 8..11  W producers: cp.async (16 B, L2-only) straight into the swizzled stage,
+//                completion reported with cp.async.mbarrier.arrive.noinc; up to S chunks ahead
+//   warp 12      one elected thread issues tcgen05.mma (accumulator in TMEM) and
 //                tcgen05.commit's each stage back to the producers
-//   warps 0..3   epilogue: tcgen05.ld (one output row per thread), bias, ReLU, row L2-norm from
-//                registers (no cross-thread reduction), staged through shared memory for
-//                coalesced 128 B stores
-// Operand tiles are written by ordinary st.shared with the swizzle applied by hand, so no TMA
-// descriptor is needed; the smem matrix descriptors follow the canonical K-major SWIZZLE_128B
-// layout (8 rows x 128 B atoms, SBO = 1024 B).
+//   epilogue     warps 0..3 read the accumulator once (tcgen05.ld, one output row per thread):
+//                bias, ReLU, sum of squares -> staging tile in the idle stage buffers; all 12
+//                producer warps then scale (row L2-norm) and store coalesced 16-byte vectors
+// No TMA descriptor is needed: the smem matrix descriptors follow the canonical K-major
+// SWIZZLE_128B layout (8 rows x 128 B atoms, SBO = 1024 B).  W should be pre-rounded to TF32
+// (pb200_round_tf32): the tensor core ignores the 13 low mantissa bits of its operands.
 #include "dense.cuh"
 
 namespace pb200 {
 
 namespace tc {
 
-constexpr int kProducerWarps = 16;
-constexpr int kProducers = kProducerWarps * 32;       // 512
+constexpr int kAWarps = 8, kBWarps = 4;
+constexpr int kAThreads = kAWarps * 32;               // 256
+constexpr int kBThreads = kBWarps * 32;               // 128
+constexpr int kProducerWarps = kAWarps + kBWarps;     // 12
+constexpr int kProducers = kProducerWarps * 32;       // 384
 constexpr int kThreads = kProducers + 32;             // + MMA warp
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                           // fp32 per 128-byte swizzle row
@@ -53,6 +59,13 @@ __device__ __forceinline__ uint32_t to_tf32(float f) {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {   // arrives when this thread's copies land
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (Blackwell: version = 1)
@@ -109,7 +122,8 @@ __host__ __device__ inline TcGeom geometry(int n_out, int T, bool pooled) {
     while (g.tmem_cols < g.umma_n) g.tmem_cols <<= 1;
     g.b_bytes = g.umma_n * 128;
     g.stage_bytes = kABytes + g.b_bytes;                        // multiples of 1024
-    const size_t lists = pooled ? (size_t)kTileM * (4 + (size_t)T * 8) : 0;
+    // raw copy of the tile's padded lists (ids, weights, 2 lengths) + compacted (id, weight, count)
+    const size_t lists = pooled ? (size_t)kTileM * (12 + (size_t)T * 16) : 0;
     const size_t fixed = 1024 /*alignment slack*/ + lists + 256 * 4 /*bias*/ + 1024 /*barriers + row scales*/;
     int s = (int)((220 * 1024 - fixed) / g.stage_bytes);
     g.stages = s > 4 ? 4 : s;
@@ -134,6 +148,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
     int* s_nv = reinterpret_cast<int*>(smem + g.off_lists);             // [128]
     int* s_id = s_nv + kTileM;                                          // [128][T]
     float* s_w = reinterpret_cast<float*>(s_id + (size_t)kTileM * T);   // [128][T]
+    int* r_len = reinterpret_cast<int*>(s_w + (size_t)kTileM * T);      // raw: [128] list_len
+    int* r_wlen = r_len + kTileM;                                       //      [128] weight_len
+    int* r_id = r_wlen + kTileM;                                        //      [128][T]
+    float* r_w = reinterpret_cast<float*>(r_id + (size_t)kTileM * T);   //      [128][T]
     float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);        // [256]
     const uint32_t bars = sbase + (uint32_t)g.off_bars;
     // barrier i: full[s] = bars + 8*s, empty[s] = bars + 8*(4+s), done = bars + 64, tmem ptr at +72
@@ -141,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(bars + 8 * s, kProducers);
+            mbar_init(bars + 8 * s, kAThreads + kBThreads);   // A: plain arrives, W: cp.async arrives
             mbar_init(bars + 8 * (4 + s), 1);
         }
         mbar_init(bars + 64, 1);
@@ -154,11 +172,16 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
     }
     if (tid < 256) s_bias[tid] = (p.bias && tid < p.n_out) ? p.bias[tid] : 0.f;
     if (pooled && warp < kProducerWarps) {
-        for (int r = warp; r < kTileM; r += kProducerWarps) {
-            const int64_t m = m0 + r;
-            int nv = 0;
-            if (m < p.n) nv = prepare_list(p.lists, m, s_id + r * T, s_w + r * T, lane);
-            if (lane == 0) s_nv[r] = nv;
+        // the tile's padded lists are one contiguous block of global memory: coalesced copy
+        const int64_t rows = min((int64_t)kTileM, p.n - m0);
+        const int nent = (int)rows * T;
+        for (int i = tid; i < nent; i += kProducers) {
+            r_id[i] = p.lists.ids[m0 * T + i];
+            r_w[i] = p.lists.weights ? p.lists.weights[m0 * T + i] : 0.f;
+        }
+        for (int i = tid; i < (int)rows; i += kProducers) {
+            r_len[i] = p.lists.list_len ? p.lists.list_len[m0 + i] : T;
+            r_wlen[i] = p.lists.weight_len ? p.lists.weight_len[m0 + i] : r_len[i];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -166,18 +189,27 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < kProducerWarps) {
-        // ===================== producers =====================
-        // Per-thread constants: which (row, 16 B chunk) pairs of the A tile (2) and of the W tile
-        // (<= 4) this thread moves every K chunk, their global row pointers and their swizzled
-        // shared-memory offsets (16 B chunk j of row r lives at chunk j ^ (r & 7)).
-        const int j = tid & 7;                          // 16-byte chunk inside the 128 B row
-        const int b_iters = (g.umma_n * 8 + kProducers - 1) / kProducers;   // <= 4
-        int a_row[2]; uint32_t a_off[2]; bool a_ok[2];
-        const float* a1p[2]; const float* a2p[2];
+    if (pooled && warp < kProducerWarps) {
+        // filter / align / renormalise each row's list with the reference class's rule
+        ListArgs la = p.lists;
+        la.ids = r_id; la.weights = p.lists.weights ? r_w : nullptr; la.list_len = r_len; la.weight_len = r_wlen;
+        for (int r = warp; r < kTileM; r += kProducerWarps) {
+            int nv = 0;
+            if (m0 + r < p.n) nv = prepare_list(la, r, s_id + r * T, s_w + r * T, lane);
+            if (lane == 0) s_nv[r] = nv;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");   // producers only
+    }
+
+    if (warp < kAWarps) {
+        // ===================== A producers =====================
+        // thread constants: 4 (row, 16 B chunk) pairs; chunk j of row r lives at chunk j ^ (r & 7)
+        const int j = tid & 7;
+        int a_row[4]; uint32_t a_off[4]; bool a_ok[4];
+        const float* a1p[4]; const float* a2p[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int r = (tid + kProducers * i) >> 3;
+        for (int i = 0; i < 4; ++i) {
+            const int r = (tid + kAThreads * i) >> 3;
             const int64_t m = m0 + r;
             a_row[i] = r;
             a_ok[i] = m < p.n;
@@ -185,23 +217,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
             a1p[i] = p.a1 + (a_ok[i] ? m : 0) * p.k1 + j * 4;
             a2p[i] = (pooled || !p.a2) ? nullptr : p.a2 + (a_ok[i] ? m : 0) * p.k2 + j * 4;
         }
-        uint32_t b_off[4]; bool b_ok[4]; const float* bp[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = (tid + kProducers * i) >> 3;
-            b_ok[i] = i < b_iters && r < p.n_out;
-            b_off[i] = (uint32_t)(kABytes + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-            bp[i] = p.w + (int64_t)(b_ok[i] ? r : 0) * K + j * 4;
-        }
-        const bool b_store3 = 3 < b_iters && ((tid + kProducers * 3) >> 3) < g.umma_n;
-        const bool b_store2 = 2 < b_iters && ((tid + kProducers * 2) >> 3) < g.umma_n;
-        const bool b_store1 = 1 < b_iters && ((tid + kProducers * 1) >> 3) < g.umma_n;
-        const bool b_store0 = ((tid) >> 3) < g.umma_n;
-
-        auto load_chunk = [&](int c, float4 (&av)[2], float4 (&bv)[4]) {
+        auto load_chunk = [&](int c, float4 (&av)[4]) {
             const int k = c * kChunkK + j * 4;          // first column of this thread's 16 B
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (a_ok[i] && k < K) {
                     if (k < p.k1) {
@@ -224,34 +243,64 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 }
                 av[i] = v;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b_ok[i] && k < K) bv[i] = __ldg(reinterpret_cast<const float4*>(bp[i] + c * kChunkK));
-            }
         };
-
-        float4 av[2], bv[4], av_n[2], bv_n[4];
-        load_chunk(0, av, bv);
-        for (int c = 0; c < nchunks; ++c) {
+        auto store_chunk = [&](int c, const float4 (&av)[4]) {
             const int s = c % g.stages, u = c / g.stages;
-            if (c + 1 < nchunks) load_chunk(c + 1, av_n, bv_n);   // in flight during wait + store
             // the MMAs that read this stage last time must have completed
             if (u > 0) mbar_wait(bars + 8 * (4 + s), (uint32_t)((u - 1) & 1));
             const uint32_t st = sbase + (uint32_t)s * g.stage_bytes;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 4; ++i)
                 st_shared_v4(st + a_off[i], to_tf32(av[i].x), to_tf32(av[i].y), to_tf32(av[i].z), to_tf32(av[i].w));
-            if (b_store0) st_shared_v4(st + b_off[0], to_tf32(bv[0].x), to_tf32(bv[0].y), to_tf32(bv[0].z), to_tf32(bv[0].w));
-            if (b_store1) st_shared_v4(st + b_off[1], to_tf32(bv[1].x), to_tf32(bv[1].y), to_tf32(bv[1].z), to_tf32(bv[1].w));
-            if (b_store2) st_shared_v4(st + b_off[2], to_tf32(bv[2].x), to_tf32(bv[2].y), to_tf32(bv[2].z), to_tf32(bv[2].w));
-            if (b_store3) st_shared_v4(st + b_off[3], to_tf32(bv[3].x), to_tf32(bv[3].y), to_tf32(bv[3].z), to_tf32(bv[3].w));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
             mbar_arrive(bars + 8 * s);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) av[i] = av_n[i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) bv[i] = bv_n[i];
+        };
+        // 3-deep register ring: two chunks of loads are in flight while one is being stored
+        float4 b0[4], b1[4], b2[4];
+        load_chunk(0, b0);
+        if (nchunks > 1) load_chunk(1, b1);
+        for (int c = 0; c < nchunks; c += 3) {
+            if (c + 2 < nchunks) load_chunk(c + 2, b2);
+            store_chunk(c, b0);
+            if (c + 1 < nchunks) {
+                if (c + 3 < nchunks) load_chunk(c + 3, b0);
+                store_chunk(c + 1, b1);
+            }
+            if (c + 2 < nchunks) {
+                if (c + 4 < nchunks) load_chunk(c + 4, b1);
+                store_chunk(c + 2, b2);
+            }
+        }
+    } else if (warp < kProducerWarps) {
+        // ===================== W producers (cp.async) =====================
+        const int t = tid - kAThreads;                  // 0..127
+        const int j = t & 7;
+        const int b_iters = (g.umma_n * 8 + kBThreads - 1) / kBThreads;   // <= 16
+        // rows n_out..umma_n-1 of the W tile are zero in every stage: written once
+        for (int s = 0; s < g.stages; ++s)
+            for (int i = 0; i < b_iters; ++i) {
+                const int r = (t + kBThreads * i) >> 3;
+                if (r >= p.n_out && r < g.umma_n)
+                    st_shared_v4(sbase + (uint32_t)s * g.stage_bytes + kABytes +
+                                 (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)), 0u, 0u, 0u, 0u);
+            }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % g.stages, u = c / g.stages;
+            if (u > 0) mbar_wait(bars + 8 * (4 + s), (uint32_t)((u - 1) & 1));
+            const uint32_t st = sbase + (uint32_t)s * g.stage_bytes + kABytes;
+            const int k = c * kChunkK + j * 4;
+            const int rem = (K - k) * 4;
+            const uint32_t nbytes = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);   // K tail: zero fill
+            const float* src = p.w + (k < K ? k : 0);
+#pragma unroll 4
+            for (int i = 0; i < b_iters; ++i) {
+                const int r = (t + kBThreads * i) >> 3;
+                if (r < p.n_out)
+                    cp_async16(st + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)),
+                               src + (int64_t)r * K, nbytes);
+            }
+            cp_async_arrive(bars + 8 * s);
         }
     } else {
         // ===================== MMA issuer (one elected lane) =====================
@@ -261,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % g.stages, u = c / g.stages;
             mbar_wait(bars + 8 * s, (uint32_t)(u & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async data -> async proxy
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
@@ -374,3 +424,20 @@ int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {
 }
 
 }  // namespace pb200
+
+namespace pb200 {
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __uint_as_float(tc::to_tf32(in[i]));
+}
+}  // namespace pb200
+
+extern "C" int pb200_round_tf32(const float* in, float* out, int64_t n, pb200_stream_t stream) {
+    using namespace pb200;
+    PB_REQUIRE(n >= 0 && (n == 0 || (in && out)), "round_tf32: bad arguments");
+    if (n == 0) return PB200_OK;
+    const int64_t blocks = ceil_div(n, 256) < kSMs * 8 ? ceil_div(n, 256) : kSMs * 8;
+    round_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+    return check_launch("round_tf32_kernel");
+}

@@ -181,10 +181,31 @@ def pool(x, ids, weights, list_len, weight_len, mode):
     return out
 
 
+_TF32_CACHE = {}
+
+
+def tf32_weight(w):
+    """`w` rounded to TF32 (pb200_round_tf32), cached per (storage, version): the tensor-core
+    path reads only the high 19 bits of its operands, so weights are rounded once, not per call."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), str(w.device))
+    hit = _TF32_CACHE.get(key)
+    if hit is None:
+        if len(_TF32_CACHE) > 256:
+            _TF32_CACHE.clear()
+        src = w.detach().contiguous()
+        hit = torch.empty_like(src)
+        check(lib().pb200_round_tf32(ptr(src), ptr(hit), src.numel(), stream_ptr(src.device)),
+              "round_tf32")
+        _TF32_CACHE[key] = hit
+    return hit
+
+
 def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N.POOL_PINSAGE,
                  flags=0, precision=N.PREC_FP32, ln_gamma=None, ln_beta=None, n=None):
     """out = epi([a1 | a2-or-pooled] @ w.T + bias).  lists = (ids, weights, list_len, weight_len)."""
     dev = N.device_of(w)
+    if precision != N.PREC_FP32:
+        w = tf32_weight(w)
     k1 = 0 if a1 is None else a1.size(1)
     if n is None:
         n = a1.size(0) if a1 is not None else (a2.size(0) if a2 is not None else lists[0].size(0))
