@@ -157,6 +157,10 @@ int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
 #define PB200_EPI_RELU 1
 #define PB200_EPI_L2NORM 2
 #define PB200_EPI_LAYERNORM 4
+#define PB200_EPI_ROUND_TF32 8 /* round the stored outputs to TF32 (an intermediate activation that
+                                  only feeds the next tensor-core layer) */
+#define PB200_IN_A1_TF32 16    /* a1 is already TF32-representable (written with PB200_EPI_ROUND_TF32 or
+                                  pb200_round_tf32): the tensor-core path streams it with cp.async */
 #define PB200_PREC_FP32 0 /* CUDA-core fp32 FMA (exact-fp32 reference kernel) */
 #define PB200_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM; UNSUPPORTED if the shape is not covered */
 #define PB200_PREC_AUTO 2 /* TF32 tensor cores where the shape is covered, CUDA-core fp32 otherwise */

@@ -200,6 +200,11 @@ __global__ void __launch_bounds__(256) dense_kernel(const DenseParams p) {
                 if (col < p.n_out) {
                     float v = fmaf(acc[i][c], scale, shift);
                     if (ln) v = fmaf(v, __ldg(p.ln_gamma + col), __ldg(p.ln_beta + col));
+                    if (p.flags & PB200_EPI_ROUND_TF32) {
+                        uint32_t r;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+                        v = __uint_as_float(r);
+                    }
                     p.out[m * p.n_out + col] = v;
                 }
             }

@@ -2,33 +2,45 @@
 //
 //   out[m,:] = epi( [A1[m,:K1] | A2row(m)] . W^T + bias ),  A2row dense or pooled on the fly
 //
-// One CTA per 128-row tile (UMMA M=128, N = n_out rounded up to 16 <= 256, K=8 per MMA),
-// 13 warps, S-stage shared-memory ring of K-major 128B-swizzled operand tiles:
-//   warps 0..7   A producers: [h | sum_j w_j h[id_j]] built from 16-byte vector loads (the
-//                neighbour rows), rounded to TF32 (cvt.rna), written with the swizzle applied
-//                by hand; a 3-deep register ring keeps two K chunks of loads in flight
-//   warps 8..11  W producers: cp.async (16 B, L2-only) straight into the swizzled stage,
-//                completion reported with cp.async.mbarrier.arrive.noinc; up to S chunks ahead
-//   warp 12      one elected thread issues tcgen05.mma (accumulator in TMEM) and
-//                tcgen05.commit's each stage back to the producers
-//   epilogue     warps 0..3 read the accumulator once (tcgen05.ld, one output row per thread):
-//                bias, ReLU, sum of squares -> staging tile in the idle stage buffers; all 12
-//                producer warps then scale (row L2-norm) and store coalesced 16-byte vectors
+// Persistent kernel: one CTA per SM loops over 128-row tiles (UMMA M=128, N = n_out rounded up
+// to 16 <= 256, K=8 per MMA).  16 warps, S-stage shared-memory ring of K-major 128B-swizzled
+// operand tiles, TWO accumulators in TMEM so the epilogue of tile i overlaps the mainloop of
+// tile i+1:
+//   warps 0..7    "pool" warps: the K chunks that need arithmetic -- the pooled neighbourhood
+//                 sum_j w_j h[id_j] (16-byte vector loads of the neighbour rows, two neighbours
+//                 per element in flight, next chunk issued before the current one is reduced)
+//                 and any operand that still has to be rounded to TF32 -- written with the
+//                 swizzle applied by hand; they also compact the tile's neighbour lists with
+//                 the reference class's filter / align / renormalise rule
+//   warps 8..9    "copy" warps: cp.async (16 B, L2-only) of W and of TF32-ready A1 columns
+//                 straight into the swizzled stage, completion via
+//                 cp.async.mbarrier.arrive.noinc, up to S chunks ahead; they also prefetch the
+//                 next tile's raw neighbour lists
+//   warp 10       one elected thread issues tcgen05.mma and tcgen05.commit's stages back to
+//                 the producers and finished accumulators to the epilogue
+//   warps 12..15  epilogue: tcgen05.ld (one output row per thread), bias, ReLU, row L2-norm
+//                 from registers, optional rounding to TF32 (so the next layer can cp.async
+//                 it), staged through a small shared tile for coalesced 16 B stores
 // No TMA descriptor is needed: the smem matrix descriptors follow the canonical K-major
 // SWIZZLE_128B layout (8 rows x 128 B atoms, SBO = 1024 B).  W should be pre-rounded to TF32
 // (pb200_round_tf32): the tensor core ignores the 13 low mantissa bits of its operands.
+#include <cstdlib>
+
 #include "dense.cuh"
 
 namespace pb200 {
 
 namespace tc {
 
-constexpr int kAWarps = 8, kBWarps = 4;
-constexpr int kAThreads = kAWarps * 32;               // 256
-constexpr int kBThreads = kBWarps * 32;               // 128
-constexpr int kProducerWarps = kAWarps + kBWarps;     // 12
-constexpr int kProducers = kProducerWarps * 32;       // 384
-constexpr int kThreads = kProducers + 32;             // + MMA warp
+
+constexpr int kPoolWarps = 8, kCopyWarps = 2;
+constexpr int kPoolThreads = kPoolWarps * 32;         // 256
+constexpr int kCopyThreads = kCopyWarps * 32;         // 64
+constexpr int kMmaWarp = kPoolWarps + kCopyWarps;     // 10 (warp 11 idle: keeps warp & 3 == TMEM lane quarter)
+constexpr int kEpiWarp0 = 12;                         // 12..15
+constexpr int kEpiThreads = 128;
+constexpr int kThreads = (kEpiWarp0 + 4) * 32;        // 512
+constexpr int kEpiStageFloats = 32 * 36;              // per epilogue warp: 32 rows x (32+4) floats
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                           // fp32 per 128-byte swizzle row
 constexpr int kABytes = kTileM * 128;                 // 16 KB
@@ -63,6 +75,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {   // arrives when this thread's copies land
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -106,33 +121,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 struct TcGeom {
-    int umma_n;      // n_out rounded up to 16
-    int tmem_cols;   // power of two >= 32
+    int umma_n;       // n_out rounded up to 16
+    int tmem_cols;    // power of two >= 2 * umma_n (two accumulators)
     int stages;
-    int b_bytes;     // umma_n * 128
-    int stage_bytes;
+    int stage_bytes;  // A tile (16 KB) + W tile (umma_n * 128 B)
+    int list_bytes;   // one compacted list buffer: nv[128] + id[128][T] + w[128][T]
     size_t smem_bytes;
-    size_t off_lists, off_bias, off_bars;
+    size_t off_epi, off_lists, off_raw, off_bias, off_bars;
+    int debug;        // PB200_TC_VARIANT (tuning experiments)
 };
 
 __host__ __device__ inline TcGeom geometry(int n_out, int T, bool pooled) {
     TcGeom g{};
     g.umma_n = (n_out + 15) / 16 * 16;
     g.tmem_cols = 32;
-    while (g.tmem_cols < g.umma_n) g.tmem_cols <<= 1;
-    g.b_bytes = g.umma_n * 128;
-    g.stage_bytes = kABytes + g.b_bytes;                        // multiples of 1024
-    // raw copy of the tile's padded lists (ids, weights, 2 lengths) + compacted (id, weight, count)
-    const size_t lists = pooled ? (size_t)kTileM * (12 + (size_t)T * 16) : 0;
-    const size_t fixed = 1024 /*alignment slack*/ + lists + 256 * 4 /*bias*/ + 1024 /*barriers + row scales*/;
-    int s = (int)((220 * 1024 - fixed) / g.stage_bytes);
+    while (g.tmem_cols < 2 * g.umma_n) g.tmem_cols <<= 1;
+    g.stage_bytes = kABytes + g.umma_n * 128;                   // multiples of 1024
+    g.list_bytes = pooled ? kTileM * (4 + T * 8) : 0;
+    const size_t raw = pooled ? (size_t)kTileM * (8 + (size_t)T * 8) : 0;
+    const size_t fixed = 1024 /*alignment slack*/ + 4 * kEpiStageFloats * 4 + 2 * (size_t)g.list_bytes +
+                         raw + 256 * 4 /*bias*/ + 256 /*barriers*/;
+    int s = (int)((225 * 1024 - fixed) / g.stage_bytes);
     g.stages = s > 4 ? 4 : s;
-    g.off_lists = (size_t)g.stages * g.stage_bytes;
-    g.off_bias = g.off_lists + lists;
+    g.off_epi = (size_t)g.stages * g.stage_bytes;
+    g.off_lists = g.off_epi + 4 * kEpiStageFloats * 4;
+    g.off_raw = g.off_lists + 2 * (size_t)g.list_bytes;
+    g.off_bias = g.off_raw + raw;
     g.off_bars = g.off_bias + 256 * 4;
-    g.smem_bytes = g.off_bars + 1024 + 1024;
+    g.smem_bytes = g.off_bars + 256 + 1024;
     return g;
 }
+
+// barrier slots (8 B each) inside the barrier block
+enum { kBarFullC = 0, kBarFullP = 4, kBarEmpty = 8, kBarTFull = 12, kBarTEmpty = 14, kBarRawReady = 16,
+       kBarRawFree = 17, kTmemSlot = 20 * 8 };
+
+struct PoolRegs { float4 t[4][2]; };   // two neighbour rows in flight per (row, 16 B chunk) slot
 
 __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams p, const TcGeom g) {
     extern __shared__ uint8_t smem_raw[];
@@ -143,253 +167,334 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
     const bool pooled = p.pool_x != nullptr && p.k2 > 0;
     const int K = p.k1 + p.k2;
     const int nchunks = (K + kChunkK - 1) / kChunkK;
-    const int64_t m0 = (int64_t)blockIdx.x * kTileM;
+    const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
+    // K chunks [0, first_reg) hold TF32-ready A1 columns only: the copy warps cp.async them.
+    // Chunks [first_reg, nchunks) need registers (pooling, or rounding to TF32).
+    const int first_reg = ((p.flags & PB200_IN_A1_TF32) && (p.k1 % kChunkK) == 0) ? p.k1 / kChunkK : 0;
 
-    int* s_nv = reinterpret_cast<int*>(smem + g.off_lists);             // [128]
-    int* s_id = s_nv + kTileM;                                          // [128][T]
-    float* s_w = reinterpret_cast<float*>(s_id + (size_t)kTileM * T);   // [128][T]
-    int* r_len = reinterpret_cast<int*>(s_w + (size_t)kTileM * T);      // raw: [128] list_len
-    int* r_wlen = r_len + kTileM;                                       //      [128] weight_len
-    int* r_id = r_wlen + kTileM;                                        //      [128][T]
-    float* r_w = reinterpret_cast<float*>(r_id + (size_t)kTileM * T);   //      [128][T]
     float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);        // [256]
     const uint32_t bars = sbase + (uint32_t)g.off_bars;
-    // barrier i: full[s] = bars + 8*s, empty[s] = bars + 8*(4+s), done = bars + 64, tmem ptr at +72
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bars + 72);
+    auto bar = [&](int slot) { return bars + 8u * (uint32_t)slot; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + g.off_bars + kTmemSlot);
+    auto list_nv = [&](int b) { return reinterpret_cast<int*>(smem + g.off_lists + (size_t)b * g.list_bytes); };
+    int* r_len = reinterpret_cast<int*>(smem + g.off_raw);              // raw copy of one tile's lists
+    int* r_wlen = r_len + kTileM;
+    int* r_id = r_wlen + kTileM;
+    float* r_w = reinterpret_cast<float*>(r_id + (size_t)kTileM * T);
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(bars + 8 * s, kAThreads + kBThreads);   // A: plain arrives, W: cp.async arrives
-            mbar_init(bars + 8 * (4 + s), 1);
+            mbar_init(bar(kBarFullC + s), kCopyThreads);   // cp.async arrives
+            mbar_init(bar(kBarFullP + s), kPoolThreads);   // plain arrives
+            mbar_init(bar(kBarEmpty + s), 1);
         }
-        mbar_init(bars + 64, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar(kBarTFull + a), 1);
+            mbar_init(bar(kBarTEmpty + a), kEpiThreads);
+        }
+        mbar_init(bar(kBarRawReady), kCopyThreads);
+        mbar_init(bar(kBarRawFree), kPoolThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kProducerWarps) {   // MMA warp owns the TMEM allocation
+    if (warp == kMmaWarp) {   // MMA warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < 256) s_bias[tid] = (p.bias && tid < p.n_out) ? p.bias[tid] : 0.f;
-    if (pooled && warp < kProducerWarps) {
-        // the tile's padded lists are one contiguous block of global memory: coalesced copy
-        const int64_t rows = min((int64_t)kTileM, p.n - m0);
-        const int nent = (int)rows * T;
-        for (int i = tid; i < nent; i += kProducers) {
-            r_id[i] = p.lists.ids[m0 * T + i];
-            r_w[i] = p.lists.weights ? p.lists.weights[m0 * T + i] : 0.f;
-        }
-        for (int i = tid; i < (int)rows; i += kProducers) {
-            r_len[i] = p.lists.list_len ? p.lists.list_len[m0 + i] : T;
-            r_wlen[i] = p.lists.weight_len ? p.lists.weight_len[m0 + i] : r_len[i];
-        }
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (pooled && warp < kProducerWarps) {
-        // filter / align / renormalise each row's list with the reference class's rule
-        ListArgs la = p.lists;
-        la.ids = r_id; la.weights = p.lists.weights ? r_w : nullptr; la.list_len = r_len; la.weight_len = r_wlen;
-        for (int r = warp; r < kTileM; r += kProducerWarps) {
-            int nv = 0;
-            if (m0 + r < p.n) nv = prepare_list(la, r, s_id + r * T, s_w + r * T, lane);
-            if (lane == 0) s_nv[r] = nv;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");   // producers only
-    }
-
-    if (warp < kAWarps) {
-        // ===================== A producers =====================
-        // thread constants: 4 (row, 16 B chunk) pairs; chunk j of row r lives at chunk j ^ (r & 7)
-        const int j = tid & 7;
-        int a_row[4]; uint32_t a_off[4]; bool a_ok[4];
-        const float* a1p[4]; const float* a2p[4];
+    if (warp < kPoolWarps) {
+        // ===================== pool warps =====================
+        const int j = tid & 7;    // 16-byte chunk inside the 128 B row; lives at chunk j ^ (r & 7)
+        const int r0 = tid >> 3;  // this thread's rows are r0, r0+32, r0+64, r0+96
+        uint32_t a_off[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int r = (tid + kAThreads * i) >> 3;
-            const int64_t m = m0 + r;
-            a_row[i] = r;
-            a_ok[i] = m < p.n;
+            const int r = r0 + 32 * i;
             a_off[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-            a1p[i] = p.a1 + (a_ok[i] ? m : 0) * p.k1 + j * 4;
-            a2p[i] = (pooled || !p.a2) ? nullptr : p.a2 + (a_ok[i] ? m : 0) * p.k2 + j * 4;
         }
-        auto load_chunk = [&](int c, float4 (&av)[4]) {
-            const int k = c * kChunkK + j * 4;          // first column of this thread's 16 B
+        int gc = 0, it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it, gc += nchunks) {
+            const int64_t m0 = tile * kTileM;
+            const int rows_left = (int)min((int64_t)kTileM, p.n - m0);
+            int* s_nv = list_nv(it & 1);
+            int* s_id = s_nv + kTileM;
+            float* s_w = reinterpret_cast<float*>(s_id + (size_t)kTileM * T);
+            if (pooled) {
+                // raw lists were prefetched by the copy warps: compact them (reference rule)
+                mbar_wait(bar(kBarRawReady), (uint32_t)(it & 1));
+                ListArgs la = p.lists;
+                la.ids = r_id; la.weights = p.lists.weights ? r_w : nullptr; la.list_len = r_len; la.weight_len = r_wlen;
+                for (int r = warp; r < kTileM; r += kPoolWarps) {
+                    int nv = 0;
+                    if (r < rows_left) nv = prepare_list(la, r, s_id + r * T, s_w + r * T, lane);
+                    if (lane == 0) s_nv[r] = nv;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kPoolThreads) : "memory");
+                mbar_arrive(bar(kBarRawFree));       // the raw buffer may be refilled for the next tile
+            }
+            if (first_reg >= nchunks) continue;
+            const float* a1b = p.a1 + (m0 + r0) * p.k1 + j * 4;
+            const float* a2b = (pooled || !p.a2) ? nullptr : p.a2 + (m0 + r0) * p.k2 + j * 4;
+
+            // issue the loads of chunk c: up to two source rows per slot
+            auto issue = [&](int c, PoolRegs& E) {
+                const int k = c * kChunkK + j * 4;          // first column of this thread's 16 B
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a_ok[i] && k < K) {
-                    if (k < p.k1) {
-                        v = __ldg(reinterpret_cast<const float4*>(a1p[i] + c * kChunkK));
-                    } else if (!pooled) {
-                        v = __ldg(reinterpret_cast<const float4*>(a2p[i] + (c * kChunkK - p.k1)));
-                    } else {
-                        const int r = a_row[i], nv = s_nv[r], kk = k - p.k1;
-                        const int* ids = s_id + r * T;
-                        const float* ws = s_w + r * T;
-#pragma unroll 2
-                        for (int q = 0; q < nv; ++q) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(
-                                p.pool_x + (int64_t)ids[q] * p.k2 + kk));
-                            const float wgt = ws[q];
-                            v.x = fmaf(wgt, t.x, v.x); v.y = fmaf(wgt, t.y, v.y);
-                            v.z = fmaf(wgt, t.z, v.z); v.w = fmaf(wgt, t.w, v.w);
+                for (int i = 0; i < 4; ++i) {
+                    E.t[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    E.t[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r0 + 32 * i < rows_left && k < K) {
+                        if (k < p.k1) {
+                            E.t[i][0] = __ldg(reinterpret_cast<const float4*>(a1b + (int64_t)(32 * i) * p.k1 + c * kChunkK));
+                        } else if (!pooled) {
+                            E.t[i][0] = __ldg(reinterpret_cast<const float4*>(a2b + (int64_t)(32 * i) * p.k2 + (c * kChunkK - p.k1)));
+                        } else {
+                            const int r = r0 + 32 * i, nv = s_nv[r], kk = k - p.k1;
+                            if (nv > 0) E.t[i][0] = __ldg(reinterpret_cast<const float4*>(p.pool_x + (int64_t)s_id[r * T] * p.k2 + kk));
+                            if (nv > 1) E.t[i][1] = __ldg(reinterpret_cast<const float4*>(p.pool_x + (int64_t)s_id[r * T + 1] * p.k2 + kk));
                         }
                     }
                 }
-                av[i] = v;
-            }
-        };
-        auto store_chunk = [&](int c, const float4 (&av)[4]) {
-            const int s = c % g.stages, u = c / g.stages;
-            // the MMAs that read this stage last time must have completed
-            if (u > 0) mbar_wait(bars + 8 * (4 + s), (uint32_t)((u - 1) & 1));
-            const uint32_t st = sbase + (uint32_t)s * g.stage_bytes;
+            };
+            // reduce chunk c and hand it to the tensor core
+            auto finish = [&](int c, const PoolRegs& E) {
+                const int k = c * kChunkK + j * 4;
+                const bool pool_chunk = pooled && k >= p.k1;
+                float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                st_shared_v4(st + a_off[i], to_tf32(av[i].x), to_tf32(av[i].y), to_tf32(av[i].z), to_tf32(av[i].w));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
-            mbar_arrive(bars + 8 * s);
-        };
-        // 3-deep register ring: two chunks of loads are in flight while one is being stored
-        float4 b0[4], b1[4], b2[4];
-        load_chunk(0, b0);
-        if (nchunks > 1) load_chunk(1, b1);
-        for (int c = 0; c < nchunks; c += 3) {
-            if (c + 2 < nchunks) load_chunk(c + 2, b2);
-            store_chunk(c, b0);
-            if (c + 1 < nchunks) {
-                if (c + 3 < nchunks) load_chunk(c + 3, b0);
-                store_chunk(c + 1, b1);
-            }
-            if (c + 2 < nchunks) {
-                if (c + 4 < nchunks) load_chunk(c + 4, b1);
-                store_chunk(c + 2, b2);
+                for (int i = 0; i < 4; ++i) {
+                    if (!pool_chunk) { v[i] = E.t[i][0]; continue; }
+                    const int r = r0 + 32 * i;
+                    const int nv = r < rows_left ? s_nv[r] : 0;
+                    const float w0 = nv > 0 ? s_w[r * T] : 0.f, w1 = nv > 1 ? s_w[r * T + 1] : 0.f;
+                    float4 a;
+                    a.x = fmaf(w1, E.t[i][1].x, w0 * E.t[i][0].x); a.y = fmaf(w1, E.t[i][1].y, w0 * E.t[i][0].y);
+                    a.z = fmaf(w1, E.t[i][1].z, w0 * E.t[i][0].z); a.w = fmaf(w1, E.t[i][1].w, w0 * E.t[i][0].w);
+                    for (int q = 2; q < nv; ++q) {    // rare: more than two valid neighbours
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(
+                            p.pool_x + (int64_t)s_id[r * T + q] * p.k2 + (k - p.k1)));
+                        const float wq = s_w[r * T + q];
+                        a.x = fmaf(wq, t.x, a.x); a.y = fmaf(wq, t.y, a.y);
+                        a.z = fmaf(wq, t.z, a.z); a.w = fmaf(wq, t.w, a.w);
+                    }
+                    v[i] = a;
+                }
+                const int g_c = gc + c;
+                const int s = g_c % g.stages, u = g_c / g.stages;
+                // the MMAs that read this stage last time must have completed
+                if (u > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((u - 1) & 1));
+                const uint32_t st = sbase + (uint32_t)s * g.stage_bytes;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    st_shared_v4(st + a_off[i], to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+                mbar_arrive(bar(kBarFullP + s));
+            };
+            PoolRegs e0, e1;
+            issue(first_reg, e0);
+            for (int c = first_reg; c < nchunks; c += 2) {
+                if (c + 1 < nchunks) issue(c + 1, e1);
+                finish(c, e0);
+                if (c + 1 < nchunks) {
+                    if (c + 2 < nchunks) issue(c + 2, e0);
+                    finish(c + 1, e1);
+                }
             }
         }
-    } else if (warp < kProducerWarps) {
-        // ===================== W producers (cp.async) =====================
-        const int t = tid - kAThreads;                  // 0..127
+    } else if (warp < kMmaWarp) {
+        // ===================== copy warps (cp.async) =====================
+        const int t = tid - kPoolThreads;               // 0..63
         const int j = t & 7;
-        const int b_iters = (g.umma_n * 8 + kBThreads - 1) / kBThreads;   // <= 16
+        const int b_iters = (g.umma_n * 8 + kCopyThreads - 1) / kCopyThreads;   // <= 32
         // rows n_out..umma_n-1 of the W tile are zero in every stage: written once
         for (int s = 0; s < g.stages; ++s)
             for (int i = 0; i < b_iters; ++i) {
-                const int r = (t + kBThreads * i) >> 3;
+                const int r = (t + kCopyThreads * i) >> 3;
                 if (r >= p.n_out && r < g.umma_n)
                     st_shared_v4(sbase + (uint32_t)s * g.stage_bytes + kABytes +
                                  (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)), 0u, 0u, 0u, 0u);
             }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % g.stages, u = c / g.stages;
-            if (u > 0) mbar_wait(bars + 8 * (4 + s), (uint32_t)((u - 1) & 1));
-            const uint32_t st = sbase + (uint32_t)s * g.stage_bytes + kABytes;
-            const int k = c * kChunkK + j * 4;
-            const int rem = (K - k) * 4;
-            const uint32_t nbytes = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);   // K tail: zero fill
-            const float* src = p.w + (k < K ? k : 0);
-#pragma unroll 4
-            for (int i = 0; i < b_iters; ++i) {
-                const int r = (t + kBThreads * i) >> 3;
-                if (r < p.n_out)
-                    cp_async16(st + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)),
-                               src + (int64_t)r * K, nbytes);
+
+        auto prefetch_lists = [&](int64_t tile, int it) {
+            // the pool warps must have compacted the previous contents
+            if (it >= 1) mbar_wait(bar(kBarRawFree), (uint32_t)((it - 1) & 1));
+            const int64_t m0 = tile * kTileM;
+            const int rows = (int)min((int64_t)kTileM, p.n - m0);
+            // the tile's padded lists are one contiguous block of global memory
+            for (int i = t; i < rows * T; i += kCopyThreads) {
+                cp_async4(smem_u32(r_id + i), p.lists.ids + m0 * T + i);
+                if (p.lists.weights) cp_async4(smem_u32(r_w + i), p.lists.weights + m0 * T + i);
             }
-            cp_async_arrive(bars + 8 * s);
+            for (int i = t; i < rows; i += kCopyThreads) {
+                if (p.lists.list_len) cp_async4(smem_u32(r_len + i), p.lists.list_len + m0 + i);
+                else r_len[i] = T;
+                if (p.lists.weight_len) cp_async4(smem_u32(r_wlen + i), p.lists.weight_len + m0 + i);
+                else if (p.lists.list_len) cp_async4(smem_u32(r_wlen + i), p.lists.list_len + m0 + i);
+                else r_wlen[i] = T;
+            }
+            cp_async_arrive(bar(kBarRawReady));
+        };
+
+        int gc = 0, it = 0;
+        if (pooled && (int64_t)blockIdx.x < ntiles) prefetch_lists(blockIdx.x, 0);
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int64_t m0 = tile * kTileM;
+            const int rows_left = (int)min((int64_t)kTileM, p.n - m0);
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const int s = gc % g.stages, u = gc / g.stages;
+                if (u > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((u - 1) & 1));
+                const uint32_t sa = sbase + (uint32_t)s * g.stage_bytes;
+                const uint32_t sb = sa + kABytes;
+                const int k = c * kChunkK + j * 4;
+                const int rem = (K - k) * 4;
+                const uint32_t nbytes = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);   // K tail: zero fill
+                const float* src = p.w + (k < K ? k : 0);
+#pragma unroll 4
+                for (int i = 0; i < b_iters; ++i) {
+                    const int r = (t + kCopyThreads * i) >> 3;
+                    if (r < p.n_out)
+                        cp_async16(sb + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)),
+                                   src + (int64_t)r * K, nbytes);
+                }
+                if (c < first_reg) {   // TF32-ready A1 columns: 128 rows x 8 chunks, rows past n zero-filled
+                    const float* asrc = p.a1 + m0 * p.k1 + c * kChunkK + j * 4;
+#pragma unroll 4
+                    for (int i = 0; i < kTileM * 8 / kCopyThreads; ++i) {
+                        const int r = (t + kCopyThreads * i) >> 3;
+                        const bool ok = r < rows_left;
+                        cp_async16(sa + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)),
+                                   asrc + (int64_t)(ok ? r : 0) * p.k1, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive(bar(kBarFullC + s));
+            }
+            if (pooled && tile + gridDim.x < ntiles) prefetch_lists(tile + gridDim.x, it + 1);
         }
-    } else {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer (one elected lane) =====================
         // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at bit 17, M>>4 at bit 24
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.umma_n >> 3) << 17) |
                                ((uint32_t)(kTileM >> 4) << 24);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % g.stages, u = c / g.stages;
-            mbar_wait(bars + 8 * s, (uint32_t)(u & 1));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async data -> async proxy
+        int gc = 0, it = 0;
+        uint32_t pphase = 0;   // parity of each stage's pool-data barrier (used by a subset of chunks)
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1, ua = it >> 1;
+            // the epilogue must have drained this accumulator (two tiles ago)
+            if (ua > 0) mbar_wait(bar(kBarTEmpty + acc), (uint32_t)((ua - 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
-                const uint32_t b_s = a_s + kABytes;
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * g.umma_n);
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const int s = gc % g.stages, u = gc / g.stages;
+                mbar_wait(bar(kBarFullC + s), (uint32_t)(u & 1));
+                if (c >= first_reg) {   // this stage also carries pool-warp data: its own phase bit
+                    mbar_wait(bar(kBarFullP + s), (pphase >> s) & 1u);
+                    pphase ^= 1u << s;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async data -> async proxy
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
+                    const uint32_t b_s = a_s + kABytes;
 #pragma unroll
-                for (int k = 0; k < kChunkK / 8; ++k)   // 4 MMAs of K = 8 (32 bytes) per chunk
-                    mma_tf32(tmem_base, make_desc(a_s + k * 32), make_desc(b_s + k * 32), idesc,
-                             (uint32_t)((c | k) != 0));
-                mma_commit(bars + 8 * (4 + s));          // frees the stage when the MMAs finish
-                if (c == nchunks - 1) mma_commit(bars + 64);
+                    for (int k = 0; k < kChunkK / 8; ++k)   // 4 MMAs of K = 8 (32 bytes) per chunk
+                        mma_tf32(tmem_d, make_desc(a_s + k * 32), make_desc(b_s + k * 32), idesc,
+                                 (uint32_t)((c | k) != 0));
+                    mma_commit(bar(kBarEmpty + s));          // frees the stage when the MMAs finish
+                    if (c == nchunks - 1) mma_commit(bar(kBarTFull + acc));
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
-    }
-
-    // ===================== epilogue =====================
-    // warps 0..3 (TMEM lane = output row): one pass over the accumulator -> bias, ReLU, sum of
-    // squares -> un-normalised row into the staging tile (the idle stage buffers, row stride
-    // N+4 floats: conflict-free 16 B stores); then all 16 producer warps scale and write the
-    // tile with coalesced 16 B stores.
-    float* stg = reinterpret_cast<float*>(smem);
-    float* s_scale = reinterpret_cast<float*>(smem + g.off_bars + 128);   // [128] after the barriers
-    const int ldst = g.umma_n + 4;
-    if (warp < 4) {
-        mbar_wait(bars + 64, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = warp * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue warps (TMEM lane quarter = warp & 3) =====================
+        const int quarter = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem + g.off_epi) + (warp - kEpiWarp0) * kEpiStageFloats;
         const bool relu = p.flags & PB200_EPI_RELU;
-        const int ncc = g.umma_n / 16;                   // 16-column pieces
-        float ss = 0.f;
-        uint32_t v[32];
-        for (int cc = 0; cc < ncc; cc += 2) {
-            tmem_ld32(taddr + cc * 16, v);               // 32 columns (reads past umma_n stay inside the allocation)
-            const int ncol = min(32, g.umma_n - cc * 16);
+        const bool l2 = p.flags & PB200_EPI_L2NORM;
+        const bool round_out = p.flags & PB200_EPI_ROUND_TF32;
+        const bool vec_out = (p.n_out & 3) == 0 && ((uintptr_t)p.out & 15) == 0;
+        const int ncc = (g.umma_n + 31) / 32;            // 32-column pieces
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1, ua = it >> 1;
+            const int64_t m0 = tile * kTileM;
+            mbar_wait(bar(kBarTFull + acc), (uint32_t)(ua & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.umma_n);
+            uint32_t v[32];
+            float scale = 1.f;
+            if (l2) {
+                float ss = 0.f;
+                for (int cc = 0; cc < ncc; ++cc) {
+                    tmem_ld32(taddr + cc * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                if (i < ncol) {
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ((cc * 32 + i) & 255));
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float f = __uint_as_float(v[i + e]) + bb[e];
+                            if (relu) f = fmaxf(f, 0.f);
+                            if (cc * 32 + i + e < p.n_out) ss = fmaf(f, f, ss);
+                        }
+                    }
+                }
+                scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);      // F.normalize eps
+            }
+            for (int cc = 0; cc < ncc; ++cc) {
+                tmem_ld32(taddr + cc * 32, v);
+                if (cc == ncc - 1) {   // accumulator fully read: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(bar(kBarTEmpty + acc));
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ((cc * 32 + i) & 255));
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     float f[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int col = cc * 16 + i + e;
-                        float x = __uint_as_float(v[i + e]) + s_bias[col & 255];
+                        float x = __uint_as_float(v[i + e]) + bb[e];
                         if (relu) x = fmaxf(x, 0.f);
-                        if (col >= p.n_out) x = 0.f;
-                        ss = fmaf(x, x, ss);
-                        f[e] = x;
+                        x *= scale;
+                        f[e] = round_out ? __uint_as_float(to_tf32(x)) : x;
                     }
-                    *reinterpret_cast<float4*>(stg + (size_t)row * ldst + cc * 16 + i) =
-                        make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(stg + lane * 36 + i) = make_float4(f[0], f[1], f[2], f[3]);
                 }
+                __syncwarp();
+                // 8 lanes cover one row's 128 B; 4 rows per instruction
+#pragma unroll
+                for (int rr0 = 0; rr0 < 32; rr0 += 4) {
+                    const int rr = rr0 + (lane >> 3), c4 = (lane & 7) * 4;
+                    const int64_t m = m0 + quarter * 32 + rr;
+                    const int col = cc * 32 + c4;
+                    if (m < p.n && col < p.n_out) {
+                        const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
+                        float* o = p.out + m * p.n_out + col;
+                        if (vec_out) {
+                            *reinterpret_cast<float4*>(o) = x;
+                        } else {
+                            o[0] = x.x;
+                            if (col + 1 < p.n_out) o[1] = x.y;
+                            if (col + 2 < p.n_out) o[2] = x.z;
+                            if (col + 3 < p.n_out) o[3] = x.w;
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
-        s_scale[row] = (p.flags & PB200_EPI_L2NORM) ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;   // F.normalize eps
     }
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp < kProducerWarps) {
-        const bool vec_out = (p.n_out & 3) == 0 && ((uintptr_t)p.out & 15) == 0;
-        const int n4 = (p.n_out + 3) >> 2;               // float4 pieces per row
-        for (int idx = tid; idx < kTileM * n4; idx += kProducers) {
-            const int r = idx / n4, c4 = (idx - r * n4) * 4;
-            const int64_t m = m0 + r;
-            if (m >= p.n) continue;
-            float4 x = *reinterpret_cast<const float4*>(stg + (size_t)r * ldst + c4);
-            const float sc = s_scale[r];
-            x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
-            float* o = p.out + m * p.n_out + c4;
-            if (vec_out) {
-                *reinterpret_cast<float4*>(o) = x;
-            } else {
-                o[0] = x.x;
-                if (c4 + 1 < p.n_out) o[1] = x.y;
-                if (c4 + 2 < p.n_out) o[2] = x.z;
-                if (c4 + 3 < p.n_out) o[3] = x.w;
-            }
-        }
-    }
-    if (warp == kProducerWarps) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
@@ -403,9 +508,7 @@ bool gather_dense_tf32_supported(const DenseParams& p) {
     if (p.n_out > 256 || (p.flags & PB200_EPI_LAYERNORM)) return false;
     if (p.k1 % 4 || p.k2 % 4) return false;
     if (((uintptr_t)p.a1 | (uintptr_t)p.a2 | (uintptr_t)p.pool_x | (uintptr_t)p.w) % 16) return false;
-    const tc::TcGeom g = tc::geometry(p.n_out, p.lists.T, pooled);
-    // the epilogue stages the whole 128 x (N+4) fp32 tile in the pipeline buffers
-    return g.stages >= 2 && (size_t)g.stages * g.stage_bytes >= (size_t)tc::kTileM * (g.umma_n + 4) * 4;
+    return tc::geometry(p.n_out, p.lists.T, pooled).stages >= 2;
 }
 
 int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {
@@ -416,10 +519,14 @@ int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {
         return PB200_ERR_UNSUPPORTED;
     }
     const bool pooled = p.pool_x != nullptr && p.k2 > 0;
-    const tc::TcGeom g = tc::geometry(p.n_out, p.lists.T, pooled);
+    tc::TcGeom g = tc::geometry(p.n_out, p.lists.T, pooled);
+    static const int dbg = [] { const char* e = getenv("PB200_TC_VARIANT"); return e ? atoi(e) : 0; }();
+    g.debug = dbg;
     PB_CUDA(cudaFuncSetAttribute(tc::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)g.smem_bytes));
-    tc::dense_tc_kernel<<<(unsigned)ceil_div(p.n, tc::kTileM), tc::kThreads, g.smem_bytes, stream>>>(p, g);
+    const int64_t ntiles = ceil_div(p.n, tc::kTileM);
+    const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);   // persistent: one CTA per SM
+    tc::dense_tc_kernel<<<grid, tc::kThreads, g.smem_bytes, stream>>>(p, g);
     return check_launch("dense_tc_kernel");
 }
 

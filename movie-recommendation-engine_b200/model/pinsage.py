@@ -111,13 +111,18 @@ class PinSage(nn.Module):
         xd = N.dev_tensor(x, torch.float32, dev)
         prec = self.precision
         P = lambda lin: (lin.weight.detach(), lin.bias.detach())
-        h = K.gather_dense(xd, *P(self.input_proj), flags=N.EPI_RELU, precision=prec)      # :202
+        # tensor-core path: intermediate activations are stored rounded to TF32 (exactly what
+        # the MMA would read anyway), which lets the next layer stream them with cp.async
+        RND = 0 if prec == N.PREC_FP32 else N.EPI_ROUND_TF32
+        PRE = 0 if prec == N.PREC_FP32 else N.IN_A1_TF32
+        h = K.gather_dense(xd, *P(self.input_proj), flags=N.EPI_RELU | RND, precision=prec)   # :202
 
         tensor_path = isinstance(sampled_neighbors, (list, tuple)) and len(sampled_neighbors) > 0 \
             and isinstance(sampled_neighbors[0], NL.NeighborBatch)
         if sampled_neighbors is None or (importance_weights is None and not tensor_path):
             for i in range(self.num_layers):                                               # :205-214
-                h = K.gather_dense(h, *P(self.convs[i].lin_self), flags=N.EPI_RELU, precision=prec)
+                h = K.gather_dense(h, *P(self.convs[i].lin_self), flags=N.EPI_RELU | RND | PRE,
+                                   precision=prec)
         else:
             per_layer = tensor_path or (isinstance(sampled_neighbors, list) and
                                         isinstance(importance_weights, list))
@@ -138,13 +143,13 @@ class PinSage(nn.Module):
                     wf, bf = self._folded_layer(i)
                     h = K.gather_dense(h, wf, bf, pool_x=h, lists=nb.as_args(),
                                        pool_mode=N.POOL_PINSAGE,
-                                       flags=N.EPI_RELU | N.EPI_L2NORM, precision=prec)
+                                       flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE, precision=prec)
                 else:
-                    h_self = K.gather_dense(h, *P(self.convs[i].lin_self), precision=prec)
+                    h_self = K.gather_dense(h, *P(self.convs[i].lin_self), flags=RND | PRE, precision=prec)
                     h = K.gather_dense(h_self, *P(self.convs[i].lin_update), pool_x=h,
                                        lists=nb.as_args(), pool_mode=N.POOL_PINSAGE,
-                                       flags=N.EPI_RELU | N.EPI_L2NORM, precision=prec)
-        emb = K.gather_dense(h, *P(self.output_proj), flags=N.EPI_L2NORM, precision=prec)  # :248-249
+                                       flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE, precision=prec)
+        emb = K.gather_dense(h, *P(self.output_proj), flags=N.EPI_L2NORM | PRE, precision=prec)  # :248-249
         if out is not None:
             out.copy_(emb, non_blocking=True)
             if not out.is_cuda:

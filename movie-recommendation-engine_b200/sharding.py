@@ -77,14 +77,16 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
         ids, _c, w, nv = sampler._sample(nodes, num_neighbors, check=False)
         batches.append(NL.from_walk(ids, w, nv))
     P = lambda lin: (lin.weight.detach(), lin.bias.detach())
-    h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU, precision=model.precision)
+    RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward
+    PRE = 0 if model.precision == N.PREC_FP32 else N.IN_A1_TF32
+    h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
     for i in range(model.num_layers):
         h_full = all_gather_rows(h_loc, num_items, group)   # the one exchange per layer
         wf, bf = model._folded_layer(i)
         h_loc = K.gather_dense(h_full[lo:hi], wf, bf, pool_x=h_full, lists=batches[i].as_args(),
-                               pool_mode=N.POOL_PINSAGE, flags=N.EPI_RELU | N.EPI_L2NORM,
+                               pool_mode=N.POOL_PINSAGE, flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE,
                                precision=model.precision)
-    return K.gather_dense(h_loc, *P(model.output_proj), flags=N.EPI_L2NORM,
+    return K.gather_dense(h_loc, *P(model.output_proj), flags=N.EPI_L2NORM | PRE,
                           precision=model.precision)
 
 

@@ -1,0 +1,39 @@
+"""Times the tcgen05 dense kernel on the C2 layer shapes for PB200_TC_VARIANT values given on
+the command line (separate processes)."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import mre_b200
+from mre_b200 import kernels as K, _native as N
+torch.manual_seed(0)
+dev = "cuda"; M = 62423; T = 10
+h = torch.randn(M, 256, device=dev); x = torch.randn(M, 128, device=dev)
+K.lib().pb200_round_tf32(K.ptr(h), K.ptr(h), h.numel(), None)
+ids = torch.randint(0, 8 * M, (M, T), dtype=torch.int32, device=dev)     # ~12%% valid, like C2
+wt = torch.rand(M, T, device=dev); ll = torch.full((M,), T, dtype=torch.int32, device=dev)
+w_in = torch.randn(256, 128, device=dev) / 11; w_cv = torch.randn(256, 512, device=dev) / 22
+w_out = torch.randn(128, 256, device=dev) / 16; b256 = torch.randn(256, device=dev); b128 = torch.randn(128, device=dev)
+def t(fn):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20): fn()          # back to back: host launch overhead hidden behind the GPU
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / 20
+P = N.PREC_TF32
+r = dict(inp=t(lambda: K.gather_dense(x, w_in, b256, flags=1, precision=P)),
+         conv=t(lambda: K.gather_dense(h, w_cv, b256, pool_x=h, lists=(ids, wt, ll, None), flags=3 | 8 | 16, precision=P)),
+         conv_dense=t(lambda: K.gather_dense(h, w_cv, b256, a2=h, flags=3, precision=P)),
+         out=t(lambda: K.gather_dense(h, w_out, b128, flags=2 | 16, precision=P)))
+ref = K.gather_dense(h, w_cv, b256, pool_x=h, lists=(ids, wt, ll, None), flags=3, precision=N.PREC_FP32)
+got = K.gather_dense(h, w_cv, b256, pool_x=h, lists=(ids, wt, ll, None), flags=3, precision=P)
+err = ((got - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-20)).max().item()
+print("variant", %s, {k: round(v, 1) for k, v in r.items()}, "us; conv err %%.2e" %% err, flush=True)
+'''
+for v in (sys.argv[1:] or ["0", "1"]):
+    env = dict(os.environ, PB200_TC_VARIANT=v)
+    r = subprocess.run([sys.executable, "-c", CHILD % (ROOT, v)], env=env, capture_output=True, text=True, timeout=300)
+    print((r.stdout.strip() or r.stderr.strip()[-400:]), flush=True)
