@@ -237,7 +237,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 asm volatile("bar.sync 1, %0;" ::"n"(kPoolThreads) : "memory");
                 mbar_arrive(bar(kBarRawFree));       // the raw buffer may be refilled for the next tile
             }
-            if (first_reg >= nchunks) continue;
             const float* a1b = p.a1 + (m0 + r0) * p.k1 + j * 4;
             const float* a2b = (pooled || !p.a2) ? nullptr : p.a2 + (m0 + r0) * p.k2 + j * 4;
 
@@ -295,8 +294,17 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
                 mbar_arrive(bar(kBarFullP + s));
             };
+            // Chunks the copy warps fill alone: step through their ring slots in order (mbarrier
+            // parity waits are only meaningful one phase apart, so no slot may be skipped).
+            auto pass = [&](int c) {
+                const int g_c = gc + c;
+                const int s = g_c % g.stages, u = g_c / g.stages;
+                if (u > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((u - 1) & 1));
+                mbar_arrive(bar(kBarFullP + s));
+            };
             PoolRegs e0, e1;
-            issue(first_reg, e0);
+            if (first_reg < nchunks) issue(first_reg, e0);   // gathers start while the MMAs run on A1
+            for (int c = 0; c < first_reg && c < nchunks; ++c) pass(c);
             for (int c = first_reg; c < nchunks; c += 2) {
                 if (c + 1 < nchunks) issue(c + 1, e1);
                 finish(c, e0);
@@ -382,7 +390,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.umma_n >> 3) << 17) |
                                ((uint32_t)(kTileM >> 4) << 24);
         int gc = 0, it = 0;
-        uint32_t pphase = 0;   // parity of each stage's pool-data barrier (used by a subset of chunks)
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1, ua = it >> 1;
             // the epilogue must have drained this accumulator (two tiles ago)
@@ -391,11 +398,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * g.umma_n);
             for (int c = 0; c < nchunks; ++c, ++gc) {
                 const int s = gc % g.stages, u = gc / g.stages;
-                mbar_wait(bar(kBarFullC + s), (uint32_t)(u & 1));
-                if (c >= first_reg) {   // this stage also carries pool-warp data: its own phase bit
-                    mbar_wait(bar(kBarFullP + s), (pphase >> s) & 1u);
-                    pphase ^= 1u << s;
-                }
+                mbar_wait(bar(kBarFullC + s), (uint32_t)(u & 1));   // copy warps (cp.async)
+                mbar_wait(bar(kBarFullP + s), (uint32_t)(u & 1));   // pool warps
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async data -> async proxy
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {

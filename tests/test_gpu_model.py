@@ -179,3 +179,30 @@ def test_tcgen05_dense_vs_cuda_core_fp32(dev, n, k1, k2, nout, pooled, flags):
     with pytest.raises(N.NativeError, match="PB200_PREC_TF32"):
         K.gather_dense(rnd(8, 6), rnd(300, 6), None, precision=N.PREC_TF32)
     assert K.gather_dense(rnd(8, 6), rnd(300, 6), None, precision=N.PREC_AUTO).shape == (8, 300)
+
+
+@pytest.mark.parametrize("fill", ["empty", "ragged", "all_valid"])
+def test_tcgen05_dense_many_tiles_per_cta(dev, fill):
+    """Persistent kernel with several 128-row tiles per CTA (> 148 tiles) and extreme list
+    shapes: all-empty tiles make the pool warps race ahead of the MMA ring (regression test for a
+    barrier-phase bug that deadlocked), all-valid lists exercise the > 2 neighbour path."""
+    from mre_b200 import kernels as K, _native as N
+    M, T = 148 * 128 * 2 + 77, 10
+    g = torch.Generator().manual_seed(7)
+    h = torch.randn(M, 64, generator=g).to(dev)
+    w, b = (torch.randn(48, 128, generator=g) / 11).to(dev), torch.randn(48, generator=g).to(dev)
+    ids = torch.randint(0, 3 * M, (M, T), generator=g, dtype=torch.int32).to(dev)
+    wt = torch.rand(M, T, generator=g).to(dev)
+    ll = torch.randint(0, T + 1, (M,), generator=g, dtype=torch.int32).to(dev)
+    if fill == "empty":
+        ll.zero_()
+    elif fill == "all_valid":
+        ids = ids % M
+    lists = (ids, wt, ll, None)
+    ref = K.gather_dense(h, w, b, pool_x=h, lists=lists, flags=3, precision=N.PREC_FP32).cpu().numpy()
+    for flags in (3, 3 | N.EPI_ROUND_TF32 | N.IN_A1_TF32):
+        hh = h
+        if flags & N.IN_A1_TF32:
+            hh = h.clone(); K.lib().pb200_round_tf32(K.ptr(hh), K.ptr(hh), hh.numel(), None)
+        got = K.gather_dense(hh, w, b, pool_x=hh, lists=lists, flags=flags, precision=N.PREC_TF32).cpu().numpy()
+        assert Hh.rel_row_err(got, ref) < 1.5e-3
