@@ -137,6 +137,8 @@ typedef enum {
     /* max over ids < M (layers.py:205-236 MaxPoolingLayer) */
     PB200_POOL_MAX = 4
 } pb200_pool_mode;
+/* OR into `mode`: store the pooled rows rounded to TF32 (they only feed a tensor-core layer) */
+#define PB200_POOL_ROUND_TF32 0x100
 
 int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
                const float* weights, const int32_t* list_len, const int32_t* weight_len,
@@ -159,6 +161,7 @@ int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
 #define PB200_EPI_LAYERNORM 4
 #define PB200_EPI_ROUND_TF32 8 /* round the stored outputs to TF32 (an intermediate activation that
                                   only feeds the next tensor-core layer) */
+#define PB200_IN_A2_TF32 32    /* same for a dense a2 */
 #define PB200_IN_A1_TF32 16    /* a1 is already TF32-representable (written with PB200_EPI_ROUND_TF32 or
                                   pb200_round_tf32): the tensor-core path streams it with cp.async */
 #define PB200_PREC_FP32 0 /* CUDA-core fp32 FMA (exact-fp32 reference kernel) */

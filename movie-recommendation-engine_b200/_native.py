@@ -65,7 +65,8 @@ SIGNATURES = {
 }
 
 POOL_PINSAGE, POOL_LAYERS, POOL_AGGREGATOR, POOL_MEAN, POOL_MAX = range(5)
-EPI_RELU, EPI_L2NORM, EPI_LAYERNORM, EPI_ROUND_TF32, IN_A1_TF32 = 1, 2, 4, 8, 16
+EPI_RELU, EPI_L2NORM, EPI_LAYERNORM, EPI_ROUND_TF32, IN_A1_TF32, IN_A2_TF32 = 1, 2, 4, 8, 16, 32
+POOL_ROUND_TF32 = 0x100
 PREC_FP32, PREC_TF32, PREC_AUTO = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "auto": PREC_AUTO}
 METRIC_IP, METRIC_L2 = 0, 1

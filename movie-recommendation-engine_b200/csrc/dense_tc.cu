@@ -12,10 +12,10 @@
 //                 and any operand that still has to be rounded to TF32 -- written with the
 //                 swizzle applied by hand; they also compact the tile's neighbour lists with
 //                 the reference class's filter / align / renormalise rule
-//   warps 8..9    "copy" warps: cp.async (16 B, L2-only) of W and of TF32-ready A1 columns
-//                 straight into the swizzled stage, completion via
-//                 cp.async.mbarrier.arrive.noinc, up to S chunks ahead; they also prefetch the
-//                 next tile's raw neighbour lists
+//   warp 8        TMA producer: one elected thread issues cp.async.bulk.tensor (SWIZZLE_128B
+//                 tensor maps) for the W tile and for TF32-ready A1 columns of every K chunk,
+//                 completion via mbarrier expect_tx / complete_tx, up to S chunks ahead
+//   warp 9        prefetches the next tile's raw neighbour lists (cp.async)
 //   warp 10       one elected thread issues tcgen05.mma and tcgen05.commit's stages back to
 //                 the producers and finished accumulators to the epilogue
 //   warps 12..15  epilogue: tcgen05.ld (one output row per thread), bias, ReLU, row L2-norm
@@ -24,6 +24,8 @@
 // No TMA descriptor is needed: the smem matrix descriptors follow the canonical K-major
 // SWIZZLE_128B layout (8 rows x 128 B atoms, SBO = 1024 B).  W should be pre-rounded to TF32
 // (pb200_round_tf32): the tensor core ignores the 13 low mantissa bits of its operands.
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint
+
 #include <cstdlib>
 
 #include "dense.cuh"
@@ -32,8 +34,18 @@ namespace pb200 {
 
 namespace tc {
 
+// ---- optional cycle accounting (make EXTRA=-DPB200_TC_PROFILE; tools/prof_dense.py) ----
+#ifdef PB200_TC_PROFILE
+__device__ unsigned long long g_prof[148][12];
+#define PROF_ADD(slot, t_begin) do { if (lane == 0) atomicAdd(&g_prof[blockIdx.x % 148][slot], (unsigned long long)(clock64() - (t_begin))); } while (0)
+#define PROF_NOW() clock64()
+#else
+#define PROF_ADD(slot, t_begin) do { } while (0)
+#define PROF_NOW() 0ll
+#endif
 
-constexpr int kPoolWarps = 8, kCopyWarps = 2;
+
+constexpr int kPoolWarps = 8, kCopyWarps = 2;       // warp 8: TMA producer, warp 9: list prefetch
 constexpr int kPoolThreads = kPoolWarps * 32;         // 256
 constexpr int kCopyThreads = kCopyWarps * 32;         // 64
 constexpr int kMmaWarp = kPoolWarps + kCopyWarps;     // 10 (warp 11 idle: keeps warp & 3 == TMEM lane quarter)
@@ -81,6 +93,18 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {   // arrives when this thread's copies land
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }"
+                 ::"r"(bar), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load: box (32 fp32 x rows) at (k0, row0) -> 128B-swizzled smem tile
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int k0, int row0,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(k0), "r"(row0), "r"(bar) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (Blackwell: version = 1)
@@ -158,7 +182,10 @@ enum { kBarFullC = 0, kBarFullP = 4, kBarEmpty = 8, kBarTFull = 12, kBarTEmpty =
 
 struct PoolRegs { float4 t[4][2]; };   // two neighbour rows in flight per (row, 16 B chunk) slot
 
-__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams p, const TcGeom g) {
+__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams p, const TcGeom g,
+                                                               const __grid_constant__ CUtensorMap tm_w,
+                                                               const __grid_constant__ CUtensorMap tm_a,
+                                                               const __grid_constant__ CUtensorMap tm_a2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -170,7 +197,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
     const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
     // K chunks [0, first_reg) hold TF32-ready A1 columns only: the copy warps cp.async them.
     // Chunks [first_reg, nchunks) need registers (pooling, or rounding to TF32).
-    const int first_reg = ((p.flags & PB200_IN_A1_TF32) && (p.k1 % kChunkK) == 0) ? p.k1 / kChunkK : 0;
+    const bool a1_tma = (p.flags & PB200_IN_A1_TF32) && p.k1 >= kChunkK && (p.k1 % kChunkK) == 0;
+    const bool a2_tma = a1_tma && (p.flags & PB200_IN_A2_TF32) && !pooled && p.a2 && (p.k2 % kChunkK) == 0;
+    const int first_reg = a2_tma ? nchunks : (a1_tma ? p.k1 / kChunkK : 0);
 
     float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);        // [256]
     const uint32_t bars = sbase + (uint32_t)g.off_bars;
@@ -184,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(bar(kBarFullC + s), kCopyThreads);   // cp.async arrives
+            mbar_init(bar(kBarFullC + s), 1);              // TMA producer: expect_tx + complete_tx
             mbar_init(bar(kBarFullP + s), kPoolThreads);   // plain arrives
             mbar_init(bar(kBarEmpty + s), 1);
         }
@@ -192,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
             mbar_init(bar(kBarTFull + a), 1);
             mbar_init(bar(kBarTEmpty + a), kEpiThreads);
         }
-        mbar_init(bar(kBarRawReady), kCopyThreads);
+        mbar_init(bar(kBarRawReady), 32);              // list-prefetch warp: cp.async arrives
         mbar_init(bar(kBarRawFree), kPoolThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -224,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
             int* s_nv = list_nv(it & 1);
             int* s_id = s_nv + kTileM;
             float* s_w = reinterpret_cast<float*>(s_id + (size_t)kTileM * T);
+            const long long t_c = PROF_NOW();
             if (pooled) {
                 // raw lists were prefetched by the copy warps: compact them (reference rule)
                 mbar_wait(bar(kBarRawReady), (uint32_t)(it & 1));
@@ -237,11 +267,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 asm volatile("bar.sync 1, %0;" ::"n"(kPoolThreads) : "memory");
                 mbar_arrive(bar(kBarRawFree));       // the raw buffer may be refilled for the next tile
             }
+            if (warp == 0) PROF_ADD(0, t_c);         // pool: wait raw lists + compaction
             const float* a1b = p.a1 + (m0 + r0) * p.k1 + j * 4;
             const float* a2b = (pooled || !p.a2) ? nullptr : p.a2 + (m0 + r0) * p.k2 + j * 4;
 
             // issue the loads of chunk c: up to two source rows per slot
             auto issue = [&](int c, PoolRegs& E) {
+                const long long t_i = PROF_NOW();
                 const int k = c * kChunkK + j * 4;          // first column of this thread's 16 B
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -259,9 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                         }
                     }
                 }
+                if (warp == 0) PROF_ADD(1, t_i);     // pool: issuing loads
             };
             // reduce chunk c and hand it to the tensor core
             auto finish = [&](int c, const PoolRegs& E) {
+                const long long t_f = PROF_NOW();
                 const int k = c * kChunkK + j * 4;
                 const bool pool_chunk = pooled && k >= p.k1;
                 float4 v[4];
@@ -285,8 +319,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 }
                 const int g_c = gc + c;
                 const int s = g_c % g.stages, u = g_c / g.stages;
+                if (warp == 0) PROF_ADD(2, t_f);     // pool: waiting for data + reduce
+                const long long t_w = PROF_NOW();
                 // the MMAs that read this stage last time must have completed
                 if (u > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((u - 1) & 1));
+                if (warp == 0) PROF_ADD(3, t_w);     // pool: waiting for a free stage
                 const uint32_t st = sbase + (uint32_t)s * g.stage_bytes;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -297,10 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
             // Chunks the copy warps fill alone: step through their ring slots in order (mbarrier
             // parity waits are only meaningful one phase apart, so no slot may be skipped).
             auto pass = [&](int c) {
+                const long long t_p = PROF_NOW();
                 const int g_c = gc + c;
                 const int s = g_c % g.stages, u = g_c / g.stages;
                 if (u > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((u - 1) & 1));
                 mbar_arrive(bar(kBarFullP + s));
+                if (warp == 0) PROF_ADD(4, t_p);     // pool: stepping through copy-only chunks
             };
             PoolRegs e0, e1;
             if (first_reg < nchunks) issue(first_reg, e0);   // gathers start while the MMAs run on A1
@@ -314,75 +353,56 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 }
             }
         }
-    } else if (warp < kMmaWarp) {
-        // ===================== copy warps (cp.async) =====================
-        const int t = tid - kPoolThreads;               // 0..63
-        const int j = t & 7;
-        const int b_iters = (g.umma_n * 8 + kCopyThreads - 1) / kCopyThreads;   // <= 32
-        // rows n_out..umma_n-1 of the W tile are zero in every stage: written once
-        for (int s = 0; s < g.stages; ++s)
-            for (int i = 0; i < b_iters; ++i) {
-                const int r = (t + kCopyThreads * i) >> 3;
-                if (r >= p.n_out && r < g.umma_n)
-                    st_shared_v4(sbase + (uint32_t)s * g.stage_bytes + kABytes +
-                                 (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)), 0u, 0u, 0u, 0u);
-            }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-
-        auto prefetch_lists = [&](int64_t tile, int it) {
-            // the pool warps must have compacted the previous contents
-            if (it >= 1) mbar_wait(bar(kBarRawFree), (uint32_t)((it - 1) & 1));
-            const int64_t m0 = tile * kTileM;
-            const int rows = (int)min((int64_t)kTileM, p.n - m0);
-            // the tile's padded lists are one contiguous block of global memory
-            for (int i = t; i < rows * T; i += kCopyThreads) {
-                cp_async4(smem_u32(r_id + i), p.lists.ids + m0 * T + i);
-                if (p.lists.weights) cp_async4(smem_u32(r_w + i), p.lists.weights + m0 * T + i);
-            }
-            for (int i = t; i < rows; i += kCopyThreads) {
-                if (p.lists.list_len) cp_async4(smem_u32(r_len + i), p.lists.list_len + m0 + i);
-                else r_len[i] = T;
-                if (p.lists.weight_len) cp_async4(smem_u32(r_wlen + i), p.lists.weight_len + m0 + i);
-                else if (p.lists.list_len) cp_async4(smem_u32(r_wlen + i), p.lists.list_len + m0 + i);
-                else r_wlen[i] = T;
-            }
-            cp_async_arrive(bar(kBarRawReady));
-        };
-
-        int gc = 0, it = 0;
-        if (pooled && (int64_t)blockIdx.x < ntiles) prefetch_lists(blockIdx.x, 0);
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int64_t m0 = tile * kTileM;
-            const int rows_left = (int)min((int64_t)kTileM, p.n - m0);
+    } else if (warp == kPoolWarps) {
+        // ===================== TMA producer (one elected lane) =====================
+        // W rows n_out..umma_n-1 and K-tail columns are outside the tensor: TMA zero-fills them
+        const uint32_t w_bytes = (uint32_t)g.umma_n * 128u, a_bytes = (uint32_t)kABytes;
+        int gc = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int row0 = (int)(tile * kTileM);
             for (int c = 0; c < nchunks; ++c, ++gc) {
                 const int s = gc % g.stages, u = gc / g.stages;
+                const long long t_e = PROF_NOW();
                 if (u > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((u - 1) & 1));
-                const uint32_t sa = sbase + (uint32_t)s * g.stage_bytes;
-                const uint32_t sb = sa + kABytes;
-                const int k = c * kChunkK + j * 4;
-                const int rem = (K - k) * 4;
-                const uint32_t nbytes = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);   // K tail: zero fill
-                const float* src = p.w + (k < K ? k : 0);
-#pragma unroll 4
-                for (int i = 0; i < b_iters; ++i) {
-                    const int r = (t + kCopyThreads * i) >> 3;
-                    if (r < p.n_out)
-                        cp_async16(sb + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)),
-                                   src + (int64_t)r * K, nbytes);
-                }
-                if (c < first_reg) {   // TF32-ready A1 columns: 128 rows x 8 chunks, rows past n zero-filled
-                    const float* asrc = p.a1 + m0 * p.k1 + c * kChunkK + j * 4;
-#pragma unroll 4
-                    for (int i = 0; i < kTileM * 8 / kCopyThreads; ++i) {
-                        const int r = (t + kCopyThreads * i) >> 3;
-                        const bool ok = r < rows_left;
-                        cp_async16(sa + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)),
-                                   asrc + (int64_t)(ok ? r : 0) * p.k1, ok ? 16u : 0u);
+                PROF_ADD(5, t_e);                    // copy: waiting for a free stage
+                const long long t_q = PROF_NOW();
+                if (lane == 0) {
+                    const uint32_t sa = sbase + (uint32_t)s * g.stage_bytes;
+                    const bool with_a = c < first_reg;   // TF32-ready A1 columns ride along
+                    mbar_expect_tx(bar(kBarFullC + s), w_bytes + (with_a ? a_bytes : 0u));
+                    tma_load_2d(sa + kABytes, &tm_w, c * kChunkK, 0, bar(kBarFullC + s));
+                    if (with_a) {
+                        if (c * kChunkK < p.k1) tma_load_2d(sa, &tm_a, c * kChunkK, row0, bar(kBarFullC + s));
+                        else tma_load_2d(sa, &tm_a2, c * kChunkK - p.k1, row0, bar(kBarFullC + s));
                     }
                 }
-                cp_async_arrive(bar(kBarFullC + s));
+                __syncwarp();
+                PROF_ADD(6, t_q);                    // copy: issuing TMA
             }
-            if (pooled && tile + gridDim.x < ntiles) prefetch_lists(tile + gridDim.x, it + 1);
+        }
+    } else if (warp == kPoolWarps + 1) {
+        // ===================== list prefetch warp =====================
+        if (pooled) {
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                // the pool warps must have compacted the previous contents
+                if (it >= 1) mbar_wait(bar(kBarRawFree), (uint32_t)((it - 1) & 1));
+                const int64_t m0 = tile * kTileM;
+                const int rows = (int)min((int64_t)kTileM, p.n - m0);
+                // the tile's padded lists are one contiguous block of global memory
+                for (int i = lane; i < rows * T; i += 32) {
+                    cp_async4(smem_u32(r_id + i), p.lists.ids + m0 * T + i);
+                    if (p.lists.weights) cp_async4(smem_u32(r_w + i), p.lists.weights + m0 * T + i);
+                }
+                for (int i = lane; i < rows; i += 32) {
+                    if (p.lists.list_len) cp_async4(smem_u32(r_len + i), p.lists.list_len + m0 + i);
+                    else r_len[i] = T;
+                    if (p.lists.weight_len) cp_async4(smem_u32(r_wlen + i), p.lists.weight_len + m0 + i);
+                    else if (p.lists.list_len) cp_async4(smem_u32(r_wlen + i), p.lists.list_len + m0 + i);
+                    else r_wlen[i] = T;
+                }
+                cp_async_arrive(bar(kBarRawReady));
+            }
         }
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer (one elected lane) =====================
@@ -398,9 +418,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * g.umma_n);
             for (int c = 0; c < nchunks; ++c, ++gc) {
                 const int s = gc % g.stages, u = gc / g.stages;
-                mbar_wait(bar(kBarFullC + s), (uint32_t)(u & 1));   // copy warps (cp.async)
+                const long long t_a = PROF_NOW();
+                mbar_wait(bar(kBarFullC + s), (uint32_t)(u & 1));   // TMA data landed
+                PROF_ADD(7, t_a);                                   // mma: waiting for cp.async data
+                const long long t_b = PROF_NOW();
                 mbar_wait(bar(kBarFullP + s), (uint32_t)(u & 1));   // pool warps
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async data -> async proxy
+                PROF_ADD(8, t_b);                                   // mma: waiting for pool data
+                const long long t_m = PROF_NOW();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t a_s = sbase + (uint32_t)s * g.stage_bytes;
@@ -413,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                     if (c == nchunks - 1) mma_commit(bar(kBarTFull + acc));
                 }
                 __syncwarp();
+                PROF_ADD(9, t_m);                                   // mma: fence + issue + commit
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -428,7 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1, ua = it >> 1;
             const int64_t m0 = tile * kTileM;
+            const long long t_x = PROF_NOW();
             mbar_wait(bar(kBarTFull + acc), (uint32_t)(ua & 1));
+            if (warp == kEpiWarp0) PROF_ADD(10, t_x);              // epilogue: waiting for an accumulator
+            const long long t_y = PROF_NOW();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.umma_n);
             uint32_t v[32];
@@ -493,6 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(const DenseParams
                 }
                 __syncwarp();
             }
+            if (warp == kEpiWarp0) PROF_ADD(11, t_y);              // epilogue: both passes
         }
     }
 
@@ -515,6 +544,36 @@ bool gather_dense_tf32_supported(const DenseParams& p) {
     return tc::geometry(p.n_out, p.lists.T, pooled).stages >= 2;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// fp32 [rows, cols] row-major -> boxes of (32 columns x box_rows rows), SWIZZLE_128B, zero OOB fill
+static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::kChunkK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {
     if (!gather_dense_tf32_supported(p)) {
         set_error("gather_dense: PB200_PREC_TF32 needs n_out <= 256, k1 %% 4 == k2 %% 4 == 0, 16 B "
@@ -526,11 +585,28 @@ int gather_dense_tf32(const DenseParams& p, cudaStream_t stream) {
     tc::TcGeom g = tc::geometry(p.n_out, p.lists.T, pooled);
     static const int dbg = [] { const char* e = getenv("PB200_TC_VARIANT"); return e ? atoi(e) : 0; }();
     g.debug = dbg;
+    alignas(64) CUtensorMap tm_w, tm_a, tm_a2;
+    const int K = p.k1 + p.k2;
+    if (!make_map(&tm_w, p.w, p.n_out, K, g.umma_n)) {
+        set_error("gather_dense: cuTensorMapEncodeTiled failed for W [%d, %d]", p.n_out, K);
+        return PB200_ERR_CUDA;
+    }
+    // A1 is streamed by TMA only when it is TF32-ready; otherwise the map is a (valid) dummy
+    const bool a_tma = (p.flags & PB200_IN_A1_TF32) && p.k1 >= tc::kChunkK && p.k1 % tc::kChunkK == 0;
+    if (!(a_tma ? make_map(&tm_a, p.a1, p.n, p.k1, tc::kTileM) : make_map(&tm_a, p.w, p.n_out, K, g.umma_n))) {
+        set_error("gather_dense: cuTensorMapEncodeTiled failed for A1 [%lld, %d]", (long long)p.n, p.k1);
+        return PB200_ERR_CUDA;
+    }
+    const bool a2_tma = a_tma && (p.flags & PB200_IN_A2_TF32) && !pooled && p.a2 && p.k2 % tc::kChunkK == 0;
+    if (!(a2_tma ? make_map(&tm_a2, p.a2, p.n, p.k2, tc::kTileM) : make_map(&tm_a2, p.w, p.n_out, K, g.umma_n))) {
+        set_error("gather_dense: cuTensorMapEncodeTiled failed for A2 [%lld, %d]", (long long)p.n, p.k2);
+        return PB200_ERR_CUDA;
+    }
     PB_CUDA(cudaFuncSetAttribute(tc::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)g.smem_bytes));
     const int64_t ntiles = ceil_div(p.n, tc::kTileM);
     const unsigned grid = (unsigned)(ntiles < kSMs ? ntiles : kSMs);   // persistent: one CTA per SM
-    tc::dense_tc_kernel<<<grid, tc::kThreads, g.smem_bytes, stream>>>(p, g);
+    tc::dense_tc_kernel<<<grid, tc::kThreads, g.smem_bytes, stream>>>(p, g, tm_w, tm_a, tm_a2);
     return check_launch("dense_tc_kernel");
 }
 
@@ -552,3 +628,12 @@ extern "C" int pb200_round_tf32(const float* in, float* out, int64_t n, pb200_st
     round_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n);
     return check_launch("round_tf32_kernel");
 }
+
+#ifdef PB200_TC_PROFILE
+extern "C" int pb200_debug_tc_profile(unsigned long long* out_host, int reset) {
+    cudaDeviceSynchronize();
+    if (out_host) cudaMemcpyFromSymbol(out_host, pb200::tc::g_prof, sizeof(unsigned long long) * 148 * 12);
+    if (reset) { static unsigned long long z[148 * 12]; cudaMemcpyToSymbol(pb200::tc::g_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -10,9 +10,16 @@
 
 namespace pb200 {
 
+__device__ __forceinline__ float round_tf32(float f) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return __uint_as_float(r);
+}
+
 template <bool kVec>
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int dim,
-                                                   ListArgs a, int64_t n, float* __restrict__ out) {
+                                                   ListArgs a, int64_t n, float* __restrict__ out,
+                                                   bool round_out) {
     extern __shared__ int32_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -39,6 +46,10 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
                         acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                     }
                 }
+                if (round_out) {
+                    acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y);
+                    acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
+                }
                 *reinterpret_cast<float4*>(o + c) = acc;
             }
         } else {
@@ -48,7 +59,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
                     const float v = __ldg(x + (int64_t)s_id[r] * dim + c);
                     acc = is_max ? fmaxf(acc, v) : fmaf(s_w[r], v, acc);
                 }
-                o[c] = acc;
+                o[c] = round_out ? round_tf32(acc) : acc;
             }
         }
         __syncwarp();
@@ -64,6 +75,8 @@ extern "C" int pb200_pool(const float* x, int64_t num_rows, int dim, const int32
                           const int32_t* weight_len, int64_t n, int max_neighbors, int mode,
                           float* out, pb200_stream_t stream) {
     PB_REQUIRE(n >= 0 && dim > 0 && max_neighbors > 0 && num_rows >= 0, "pool: bad sizes");
+    const bool round_out = mode & PB200_POOL_ROUND_TF32;
+    mode &= ~PB200_POOL_ROUND_TF32;
     PB_REQUIRE(mode >= PB200_POOL_PINSAGE && mode <= PB200_POOL_MAX, "pool: unknown mode %d", mode);
     if (n == 0) return PB200_OK;
     PB_REQUIRE(x && ids && out, "pool: null pointer");
@@ -78,6 +91,6 @@ extern "C" int pb200_pool(const float* x, int64_t num_rows, int dim, const int32
     int64_t blocks = ceil_div(n, wpb);
     const int64_t cap = (int64_t)kSMs * 16;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(x, dim, a, n, out);
+    kern<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(x, dim, a, n, out, round_out);
     return check_launch("pool_kernel");
 }

@@ -71,6 +71,10 @@ class PinSage(nn.Module):
         self.importance_pooling = ImportancePooling()
         self.output_proj = nn.Linear(hidden_channels, out_channels)
         self.fold = True                 # fold lin_self into lin_update (one GEMM per layer)
+        # Tensor-core path: True gathers the neighbour rows inside the GEMM kernel's producer
+        # warps (one launch per layer); False runs the pooling kernel first and streams both
+        # halves of K through TMA (two launches, measured faster: see DESIGN.md section 4).
+        self.fuse_pool = False
         # PREC_AUTO: tcgen05 kind::tf32 tensor cores (fp32 accumulate) where the layer shape is
         # covered, CUDA-core fp32 otherwise; PREC_FP32 forces the exact-fp32 kernels.
         self.precision = N.PREC_AUTO
@@ -139,7 +143,13 @@ class PinSage(nn.Module):
                 if len(nb) != h.size(0):
                     raise RuntimeError(f"layer {i}: {len(nb)} neighbour lists for {h.size(0)} rows "
                                        "(torch.cat would fail in the reference, :238)")
-                if self.fold:
+                if self.fold and prec != N.PREC_FP32 and not self.fuse_pool:
+                    wf, bf = self._folded_layer(i)
+                    h_neigh = K.pool(h, *nb.as_args(), N.POOL_PINSAGE | N.POOL_ROUND_TF32)
+                    h = K.gather_dense(h, wf, bf, a2=h_neigh,
+                                       flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
+                                       precision=prec)
+                elif self.fold:
                     wf, bf = self._folded_layer(i)
                     h = K.gather_dense(h, wf, bf, pool_x=h, lists=nb.as_args(),
                                        pool_mode=N.POOL_PINSAGE,

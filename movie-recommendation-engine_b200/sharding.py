@@ -83,6 +83,12 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     for i in range(model.num_layers):
         h_full = all_gather_rows(h_loc, num_items, group)   # the one exchange per layer
         wf, bf = model._folded_layer(i)
+        if model.precision != N.PREC_FP32 and not model.fuse_pool:      # see PinSage.forward
+            h_neigh = K.pool(h_full, *batches[i].as_args(), N.POOL_PINSAGE | N.POOL_ROUND_TF32)
+            h_loc = K.gather_dense(h_full[lo:hi], wf, bf, a2=h_neigh,
+                                   flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
+                                   precision=model.precision)
+            continue
         h_loc = K.gather_dense(h_full[lo:hi], wf, bf, pool_x=h_full, lists=batches[i].as_args(),
                                pool_mode=N.POOL_PINSAGE, flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE,
                                precision=model.precision)

@@ -87,11 +87,11 @@ def test_forward_vs_reference_golden(dev, precision):
     x = torch.from_numpy(g["x"]).to(dev)
     assert Hh.rel_row_err(model(x).cpu().numpy(), g["emb_mlp"]) < TOL                 # MLP branch
     nb0, wt0, nb1, wt1 = Hh.lists_from_json(g, "nb0", "wt0", "nb1", "wt1")
-    for fold in (True, False):
-        model.fold = fold
+    for fold, fuse in ((True, False), (True, True), (False, True)):
+        model.fold, model.fuse_pool = fold, fuse
         got = model(x, None, [nb0, nb1], [wt0, wt1]).cpu().numpy()
-        assert Hh.rel_row_err(got, g["emb_lists"]) < TOL, f"fold={fold}"
-    model.fold = True
+        assert Hh.rel_row_err(got, g["emb_lists"]) < TOL, f"fold={fold} fuse_pool={fuse}"
+    model.fold, model.fuse_pool = True, False
     # CPU input in, CPU tensor out
     assert model(torch.from_numpy(g["x"])).device.type == "cpu"
 

@@ -26,7 +26,8 @@ def t(fn):
 P = N.PREC_TF32
 r = dict(inp=t(lambda: K.gather_dense(x, w_in, b256, flags=1, precision=P)),
          conv=t(lambda: K.gather_dense(h, w_cv, b256, pool_x=h, lists=(ids, wt, ll, None), flags=3 | 8 | 16, precision=P)),
-         conv_dense=t(lambda: K.gather_dense(h, w_cv, b256, a2=h, flags=3, precision=P)),
+         conv_dense=t(lambda: K.gather_dense(h, w_cv, b256, a2=h, flags=3 | 8 | 16 | 32, precision=P)),
+         pool=t(lambda: K.pool(h, ids, wt, ll, None, 0x100)),
          out=t(lambda: K.gather_dense(h, w_out, b128, flags=2 | 16, precision=P)))
 ref = K.gather_dense(h, w_cv, b256, pool_x=h, lists=(ids, wt, ll, None), flags=3, precision=N.PREC_FP32)
 got = K.gather_dense(h, w_cv, b256, pool_x=h, lists=(ids, wt, ll, None), flags=3, precision=P)
