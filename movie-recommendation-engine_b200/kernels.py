@@ -185,19 +185,25 @@ _TF32_CACHE = {}
 
 
 def tf32_weight(w):
-    """`w` rounded to TF32 (pb200_round_tf32), cached per (storage, version): the tensor-core
-    path reads only the high 19 bits of its operands, so weights are rounded once, not per call."""
-    key = (w.data_ptr(), w._version, tuple(w.shape), str(w.device))
+    """`w` rounded to TF32 (pb200_round_tf32), cached per tensor object and version: the
+    tensor-core path reads only the high 19 bits of its operands, so weights are rounded once,
+    not per call.  Entries die with their source tensor (weak reference), so a new tensor that
+    happens to reuse freed memory can never hit a stale entry."""
+    import weakref
+    key = id(w)
     hit = _TF32_CACHE.get(key)
-    if hit is None:
-        if len(_TF32_CACHE) > 256:
-            _TF32_CACHE.clear()
-        src = w.detach().contiguous()
-        hit = torch.empty_like(src)
-        check(lib().pb200_round_tf32(ptr(src), ptr(hit), src.numel(), stream_ptr(src.device)),
-              "round_tf32")
-        _TF32_CACHE[key] = hit
-    return hit
+    if hit is not None and hit[0]() is w and hit[1] == (w._version, w.data_ptr()):
+        return hit[2]
+    src = w.detach().contiguous()
+    out = torch.empty_like(src)
+    check(lib().pb200_round_tf32(ptr(src), ptr(out), src.numel(), stream_ptr(src.device)),
+          "round_tf32")
+    try:
+        ref = weakref.ref(w, lambda _r, k=key: _TF32_CACHE.pop(k, None))
+    except TypeError:
+        return out
+    _TF32_CACHE[key] = (ref, (w._version, w.data_ptr()), out)
+    return out
 
 
 def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N.POOL_PINSAGE,

@@ -42,10 +42,9 @@ class GraphConv(nn.Module):
                                       "model/pinsage.py:53) is outside the B200 hot path")
         dev = N.device_of(self.lin_self.weight)
         x = N.dev_tensor(x, torch.float32, dev)
-        h_self = K.gather_dense(x, self.lin_self.weight.detach(), self.lin_self.bias.detach())
+        h_self = K.gather_dense(x, self.lin_self.weight, self.lin_self.bias)
         zeros = torch.zeros_like(h_self)                       # :50
-        return K.gather_dense(h_self, self.lin_update.weight.detach(),
-                              self.lin_update.bias.detach(), a2=zeros,
+        return K.gather_dense(h_self, self.lin_update.weight, self.lin_update.bias, a2=zeros,
                               flags=N.EPI_RELU | N.EPI_L2NORM)
 
 
@@ -114,7 +113,7 @@ class PinSage(nn.Module):
         in_dev = x.device if isinstance(x, torch.Tensor) else torch.device("cpu")
         xd = N.dev_tensor(x, torch.float32, dev)
         prec = self.precision
-        P = lambda lin: (lin.weight.detach(), lin.bias.detach())
+        P = lambda lin: (lin.weight, lin.bias)     # Parameter objects: identity keys the TF32 weight cache
         # tensor-core path: intermediate activations are stored rounded to TF32 (exactly what
         # the MMA would read anyway), which lets the next layer stream them with cp.async
         RND = 0 if prec == N.PREC_FP32 else N.EPI_ROUND_TF32

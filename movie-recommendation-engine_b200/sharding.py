@@ -76,7 +76,7 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     for _ in range(model.num_layers):                       # same epochs on every rank
         ids, _c, w, nv = sampler._sample(nodes, num_neighbors, check=False)
         batches.append(NL.from_walk(ids, w, nv))
-    P = lambda lin: (lin.weight.detach(), lin.bias.detach())
+    P = lambda lin: (lin.weight, lin.bias)     # Parameter objects: identity keys the TF32 weight cache
     RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward
     PRE = 0 if model.precision == N.PREC_FP32 else N.IN_A1_TF32
     h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
