@@ -177,6 +177,63 @@ __device__ __forceinline__ void sort8_desc(uint32_t (&v)[8]) {
     cex(v[1], v[2]); cex(v[3], v[4]); cex(v[5], v[6]);
 }
 
+// Register top-T (slots <= 512, W*L <= 255, T <= 32): key = count<<17 | (255-first)<<9 | slot, so
+// the winner's node id is one broadcast shared-memory load; keys are sorted once per lane in
+// registers and every round pops the warp-wide maximum.  Lane j keeps the j-th winner: the
+// results leave the warp as three coalesced stores.
+template <bool kWide>
+__device__ __forceinline__ void select_topt_regs(const WalkParams& p, const int32_t* keys, int64_t s,
+                                                 int lane) {
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(keys + p.slots);
+    const uint32_t* first = cnt + p.slots;
+    uint32_t k[8], k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int slot = i * 32 + lane;
+        const uint32_t c = cnt[slot];
+        k[i] = c ? ((c << 17) | ((255u - first[slot]) << 9) | (uint32_t)slot) : 0u;
+        k2[i] = 0u;
+        if (kWide) {
+            const uint32_t c2 = cnt[slot + 256];
+            k2[i] = c2 ? ((c2 << 17) | ((255u - first[slot + 256]) << 9) | (uint32_t)(slot + 256)) : 0u;
+        }
+    }
+    sort8_desc(k);
+    if (kWide) sort8_desc(k2);
+    int my_id = -1; uint32_t my_cnt = 0, total = 0;
+    int nvalid = 0;
+    for (int j = 0; j < p.T; ++j) {
+        const uint32_t head = kWide ? max(k[0], k2[0]) : k[0];
+        const uint32_t m = __reduce_max_sync(kFull, head);
+        if (m == 0) break;                     // fewer than T distinct nodes
+        if (k[0] == m) {                       // unique winner pops its head
+#pragma unroll
+            for (int i = 0; i < 7; ++i) k[i] = k[i + 1];
+            k[7] = 0u;
+        } else if (kWide && k2[0] == m) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) k2[i] = k2[i + 1];
+            k2[7] = 0u;
+        }
+        const uint32_t c = m >> 17;
+        const int node = keys[m & 511u];       // broadcast
+        total += c;
+        my_id = lane == j ? node : my_id;
+        my_cnt = lane == j ? c : my_cnt;
+        ++nvalid;
+    }
+    if (lane < p.T) {
+        const bool has = lane < nvalid;
+        const int64_t o = s * p.T + lane;
+        p.out_ids[o] = has ? my_id : -1;
+        p.out_counts[o] = has ? (int32_t)my_cnt : 0;
+        // float64 division like the reference, then the fp32 cast that
+        // torch.tensor(list) applies in ImportancePooling (model/pinsage.py:140)
+        p.out_w[o] = has ? (float)((double)my_cnt / (double)total) : 0.0f;
+    }
+    if (lane == 0) p.out_nvalid[s] = nvalid;
+}
+
 // Warp-level structure: one warp per start node (warps never wait for each other).  Lane l
 // runs walks l, l+32, ...: the start node, its table and its row are warp-uniform, so the
 // first step's loads are broadcasts.  (Measured alternatives, tools/tune_walk.py: two starts
@@ -247,55 +304,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
             uint32_t total = 0;
             int nvalid = 0;
             if (kRegSel && p.slots <= 512 && V <= 255 && p.T <= 32) {
-                // fast path: key = count<<16 | (255-first)<<8... packed with the slot index so
-                // that the winner's node id is one broadcast shared-memory load; keys are sorted
-                // once per lane in registers and every round pops the warp-wide maximum.  Lane j
-                // keeps the j-th winner: the results leave the warp as three coalesced stores.
-                uint32_t k[8], k2[8];
-                const bool wide = p.slots == 512;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int slot = i * 32 + lane;
-                    const uint32_t c = cnt[slot];
-                    k[i] = c ? ((c << 17) | ((255u - first[slot]) << 9) | (uint32_t)slot) : 0u;
-                    k2[i] = 0u;
-                    if (wide) {
-                        const uint32_t c2 = cnt[slot + 256];
-                        k2[i] = c2 ? ((c2 << 17) | ((255u - first[slot + 256]) << 9) | (uint32_t)(slot + 256)) : 0u;
-                    }
-                }
-                sort8_desc(k);
-                if (wide) sort8_desc(k2);
-                int my_id = -1; uint32_t my_cnt = 0;
-                for (int j = 0; j < p.T; ++j) {
-                    const uint32_t head = max(k[0], k2[0]);
-                    const uint32_t m = __reduce_max_sync(kFull, head);
-                    if (m == 0) break;                     // fewer than T distinct nodes
-                    if (k[0] == m) {                       // unique winner pops its head
-#pragma unroll
-                        for (int i = 0; i < 7; ++i) k[i] = k[i + 1];
-                        k[7] = 0u;
-                    } else if (k2[0] == m) {
-#pragma unroll
-                        for (int i = 0; i < 7; ++i) k2[i] = k2[i + 1];
-                        k2[7] = 0u;
-                    }
-                    const uint32_t c = m >> 17;
-                    const int node = keys[m & 511u];       // broadcast
-                    total += c;
-                    my_id = lane == j ? node : my_id;
-                    my_cnt = lane == j ? c : my_cnt;
-                    ++nvalid;
-                }
-                if (lane < p.T) {
-                    const bool has = lane < nvalid;
-                    o_ids[lane] = has ? my_id : -1;
-                    o_cnt[lane] = has ? (int32_t)my_cnt : 0;
-                    // float64 division like the reference, then the fp32 cast that
-                    // torch.tensor(list) applies in ImportancePooling (model/pinsage.py:140)
-                    o_w[lane] = has ? (float)((double)my_cnt / (double)total) : 0.0f;
-                }
-                if (lane == 0) p.out_nvalid[s] = nvalid;
+                if (p.slots == 512) select_topt_regs<true>(p, keys, s, lane);
+                else select_topt_regs<false>(p, keys, s, lane);
                 __syncwarp();
                 continue;
             } else {
@@ -339,6 +349,17 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
         __syncwarp();
     }
 }
+
+// Measured and rejected (B200, config C2, tools/tune_walk.py; baseline 0.360 ms per launch):
+//   * 2 or 4 walks per lane with the loads of every stage (meta / index level / leaf) issued
+//     back to back: 0.361-0.524 ms.  More requests in flight do not help: ncu shows the LSU
+//     data pipe (66 % of peak wavefronts -- every lane of a divergent 32 B load is its own
+//     wavefront -- plus 16 % from the shared-memory atomics) and the issue slots (59 %) as the
+//     loaded units, not memory latency or DRAM bandwidth (28 %).
+//   * staging the start node's row in shared memory (coalesced 16 B copies) and running the
+//     first step of all W walks as a binary search there: 0.41-0.50 ms (9 dependent LDS per
+//     walk with bank conflicts cost more pipe cycles than the 2-3 index/leaf loads they
+//     replace, and the extra 2-4 KB per warp lowers occupancy).
 
 template <int kMode, bool kBin, bool kRegSel, int kMinBlocks>
 static int launch_variant(const WalkParams& p, int warps, size_t smem, cudaStream_t stream) {
