@@ -198,6 +198,22 @@ int pb200_topk(const float* queries, int64_t nq, const float* items, int64_t nx,
                int metric, const int32_t* exclude_ids, int32_t id_offset, float* out_scores,
                int32_t* out_ids, void* workspace, size_t workspace_bytes, pb200_stream_t stream);
 
+/* Same contract and BITWISE the same results as pb200_topk, computed on the tensor cores:
+ * tcgen05 kind::tf32 scoring GEMM fused with a streaming per-query shortlist (ks = 16 or 32
+ * items per query and item split), exact fp32 re-rank of the shortlist with pb200_topk's own
+ * arithmetic, and a certificate (|tf32 - fp32 score| <= |q| max|x~ - x| + |q~ - q| max|x~| + slack,
+ * from the measured TF32 rounding residuals of the operands) that no item outside the
+ * shortlist can enter the top-k; queries that fail it are re-run by the fp32
+ * kernel from a device-side list (no host sync).  Covers dim % 4 == 0, dim <= 256,
+ * k (+1 with exclude_ids) <= 24 (pb200_topk_tc_supported); PB200_ERR_UNSUPPORTED otherwise.
+ * queries / items 16-byte aligned.  stats_out: optional DEVICE int32[1] = queries re-run in fp32. */
+int pb200_topk_tc_supported(int64_t nq, int64_t nx, int dim, int k, int has_exclude);
+size_t pb200_topk_tc_workspace_bytes(int64_t nq, int64_t nx, int dim, int k);
+int pb200_topk_tc(const float* queries, int64_t nq, const float* items, int64_t nx, int dim, int k,
+                  int metric, const int32_t* exclude_ids, int32_t id_offset, float* out_scores,
+                  int32_t* out_ids, void* workspace, size_t workspace_bytes, int32_t* stats_out,
+                  pb200_stream_t stream);
+
 /* Merge of per-shard candidate lists (multi-GPU: after the NCCL all-gather).
  * scores float32 [nq,c], ids int32 [nq,c] (id < 0 = padding); largest != 0 for IP. */
 int pb200_topk_merge(const float* scores, const int32_t* ids, int64_t nq, int c, int k,

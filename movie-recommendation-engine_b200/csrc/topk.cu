@@ -8,7 +8,7 @@
 // (lane r holds rank r), so HBM/L2 traffic is the operands only.
 // Items can be split across blockIdx.y; the per-split lists are merged by the same warp
 // top-k under the (score, id) total order, which makes results tiling- and shard-invariant.
-#include "common.cuh"
+#include "topk.cuh"
 
 namespace pb200 {
 
@@ -36,7 +36,16 @@ struct TopkParams {
     int k_total, col_off;
     int splits; int64_t split_len;
     float* __restrict__ part_bad; int32_t* __restrict__ part_ids;   // [nq, splits, 32]
+    // optional query selection (pb200_topk_tc re-runs only its uncertified queries): slot i of
+    // this launch is query qsel[qsel_base + i], for i < min(nq, *qsel_count - qsel_base)
+    const int32_t* __restrict__ qsel; const int32_t* __restrict__ qsel_count; int64_t qsel_base;
 };
+
+__device__ __forceinline__ int64_t sel_count(const int32_t* qsel, const int32_t* cnt, int64_t base, int64_t nq) {
+    if (!qsel) return nq;
+    const int64_t c = (int64_t)*cnt - base;
+    return c < nq ? (c < 0 ? 0 : c) : nq;
+}
 
 __global__ void __launch_bounds__(256) topk_tile_kernel(const TopkParams p) {
     __shared__ __align__(16) float q_s[TK][TQ + 4];
@@ -48,15 +57,18 @@ __global__ void __launch_bounds__(256) topk_tile_kernel(const TopkParams p) {
     const int64_t xs = (int64_t)blockIdx.y * p.split_len;
     const int64_t xe = min(p.nx, xs + p.split_len);
     const int k = p.k_pass;
+    const int64_t nq_eff = sel_count(p.qsel, p.qsel_count, p.qsel_base, p.nq);
+    if (q0 >= nq_eff) return;
 
     TopkLane best[8];
     float fl_bad[8]; int fl_id[8]; float qn[8]; int excl[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         best[r].bad = INFINITY; best[r].id = INT_MAX;
-        const int64_t qi = q0 + warp * 8 + r;
+        const int64_t qs = q0 + warp * 8 + r;
         fl_bad[r] = -INFINITY; fl_id[r] = -1; qn[r] = 0.f; excl[r] = -1;
-        if (qi < p.nq) {
+        if (qs < nq_eff) {
+            const int64_t qi = p.qsel ? p.qsel[p.qsel_base + qs] : qs;
             if (p.col_off > 0) {
                 const float s = p.final_scores[qi * p.k_total + p.col_off - 1];
                 fl_bad[r] = p.metric == PB200_METRIC_IP ? -s : s;
@@ -81,8 +93,9 @@ __global__ void __launch_bounds__(256) topk_tile_kernel(const TopkParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int kc = k0 + kk + i;
-                    const int64_t qi = q0 + r, xi = x0 + r;
-                    q_s[kk + i][r] = (qi < p.nq && kc < p.d) ? __ldg(p.q + qi * p.d + kc) : 0.f;
+                    const int64_t qs = q0 + r, xi = x0 + r;
+                    const int64_t qi = (p.qsel && qs < nq_eff) ? p.qsel[p.qsel_base + qs] : qs;
+                    q_s[kk + i][r] = (qs < nq_eff && kc < p.d) ? __ldg(p.q + qi * p.d + kc) : 0.f;
                     x_s[kk + i][r] = (xi < xe && kc < p.d) ? __ldg(p.x + xi * p.d + kc) : 0.f;
                 }
             }
@@ -107,8 +120,7 @@ __global__ void __launch_bounds__(256) topk_tile_kernel(const TopkParams p) {
         // each warp scans its 8 query rows; lane covers items lane and lane+32 of the tile
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int64_t qi = q0 + warp * 8 + r;
-            if (qi >= p.nq) break;  // warp-uniform
+            if (q0 + warp * 8 + r >= nq_eff) break;  // warp-uniform
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col = lane + 32 * h;
@@ -127,8 +139,8 @@ __global__ void __launch_bounds__(256) topk_tile_kernel(const TopkParams p) {
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const int64_t qi = q0 + warp * 8 + r;
-        if (qi >= p.nq) break;
+        const int64_t qi = q0 + warp * 8 + r;   // slot index: partial lists are slot-major
+        if (qi >= nq_eff) break;
         const int64_t o = (qi * p.splits + blockIdx.y) * 32 + lane;
         p.part_bad[o] = best[r].bad;
         p.part_ids[o] = best[r].id == INT_MAX ? -1 : best[r].id;
@@ -142,17 +154,19 @@ struct MergeParams {
     int k_pass, k_total, col_off, use_floor;
     float* __restrict__ out_scores; int32_t* __restrict__ out_ids;
     int out_hamming;  // unused here (kept for symmetry with lsh.cu)
+    const int32_t* __restrict__ qsel; const int32_t* __restrict__ qsel_count; int64_t qsel_base;
 };
 
 __global__ void __launch_bounds__(256) topk_merge_kernel(const MergeParams p) {
     const int lane = threadIdx.x & 31;
-    const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (qi >= p.nq) return;
+    const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // slot
+    if (qi >= sel_count(p.qsel, p.qsel_count, p.qsel_base, p.nq)) return;
+    const int64_t qo = p.qsel ? p.qsel[p.qsel_base + qi] : qi;                            // output row
     TopkLane e; e.bad = INFINITY; e.id = INT_MAX;
     float fb = -INFINITY; int fi = -1;
     if (p.use_floor && p.col_off > 0) {
-        const float s = p.out_scores[qi * p.k_total + p.col_off - 1];
-        fi = p.out_ids[qi * p.k_total + p.col_off - 1];
+        const float s = p.out_scores[qo * p.k_total + p.col_off - 1];
+        fi = p.out_ids[qo * p.k_total + p.col_off - 1];
         fb = p.largest ? -s : s;
         if (fi < 0) { fb = INFINITY; fi = INT_MAX; }
     }
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const MergeParams p) {
         topk_offer(e, bad, id, valid, p.k_pass, lane);
     }
     if (lane < p.k_pass) {
-        const int64_t o = qi * p.k_total + p.col_off + lane;
+        const int64_t o = qo * p.k_total + p.col_off + lane;
         const bool has = e.id != INT_MAX;
         p.out_ids[o] = has ? e.id : -1;
         p.out_scores[o] = has ? (p.largest ? -e.bad : e.bad) : (p.largest ? -INFINITY : INFINITY);
@@ -182,6 +196,44 @@ static int choose_splits(int64_t nq, int64_t nx) {
     if (s > max_by_len) s = max_by_len;
     if (s > 64) s = 64;
     return (int)(s < 1 ? 1 : s);
+}
+
+int row_sqnorm_run(const float* x, int64_t n, int d, float* out, cudaStream_t stream) {
+    if (n <= 0) return PB200_OK;
+    row_sqnorm_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, stream>>>(x, n, d, out);
+    return check_launch("row_sqnorm_kernel");
+}
+
+// All passes (32 ranks each) of the fp32 tile kernel + merge for nq query slots.
+int topk_fp32_run(const float* queries, int64_t nq, const float* items, int64_t nx, int dim, int k,
+                  int metric, const float* qn, const float* xn, const int32_t* exclude_ids,
+                  int32_t id_offset, float* out_scores, int32_t* out_ids, float* part_bad,
+                  int32_t* part_ids, int splits, const int32_t* qsel, const int32_t* qsel_count,
+                  int64_t qsel_base, cudaStream_t stream) {
+    const int64_t split_len = ceil_div(ceil_div(nx > 0 ? nx : 1, splits), TX) * TX;
+    for (int col = 0; col < k; col += 32) {
+        TopkParams p{};
+        p.q = queries; p.nq = nq; p.x = items; p.nx = nx; p.d = dim;
+        p.k_pass = k - col < 32 ? k - col : 32; p.metric = metric; p.qn = qn; p.xn = xn;
+        p.exclude = exclude_ids; p.id_offset = id_offset;
+        p.final_scores = out_scores; p.final_ids = out_ids; p.k_total = k; p.col_off = col;
+        p.splits = splits; p.split_len = split_len; p.part_bad = part_bad; p.part_ids = part_ids;
+        p.qsel = qsel; p.qsel_count = qsel_count; p.qsel_base = qsel_base;
+        dim3 grid((unsigned)ceil_div(nq, TQ), splits);
+        topk_tile_kernel<<<grid, 256, 0, stream>>>(p);
+        int rc = check_launch("topk_tile_kernel");
+        if (rc) return rc;
+        MergeParams m{};
+        m.vals = part_bad; m.ids = part_ids; m.nq = nq; m.c = splits * 32; m.vals_are_bad = 1;
+        m.largest = metric == PB200_METRIC_IP; m.k_pass = p.k_pass; m.k_total = k;
+        m.col_off = col; m.use_floor = 0;  // partial lists are already beyond the floor
+        m.out_scores = out_scores; m.out_ids = out_ids;
+        m.qsel = qsel; m.qsel_count = qsel_count; m.qsel_base = qsel_base;
+        topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(m);
+        rc = check_launch("topk_merge_kernel");
+        if (rc) return rc;
+    }
+    return PB200_OK;
 }
 
 }  // namespace pb200
@@ -228,28 +280,8 @@ extern "C" int pb200_topk(const float* queries, int64_t nq, const float* items, 
             if (rc) return rc;
         }
     }
-    int64_t split_len = ceil_div(ceil_div(nx > 0 ? nx : 1, splits), TX) * TX;
-    for (int col = 0; col < k; col += 32) {
-        TopkParams p{};
-        p.q = queries; p.nq = nq; p.x = items; p.nx = nx; p.d = dim;
-        p.k_pass = k - col < 32 ? k - col : 32; p.metric = metric; p.qn = qn; p.xn = xn;
-        p.exclude = exclude_ids; p.id_offset = id_offset;
-        p.final_scores = out_scores; p.final_ids = out_ids; p.k_total = k; p.col_off = col;
-        p.splits = splits; p.split_len = split_len; p.part_bad = part_bad; p.part_ids = part_ids;
-        dim3 grid((unsigned)ceil_div(nq, TQ), splits);
-        topk_tile_kernel<<<grid, 256, 0, stream>>>(p);
-        int rc = check_launch("topk_tile_kernel");
-        if (rc) return rc;
-        MergeParams m{};
-        m.vals = part_bad; m.ids = part_ids; m.nq = nq; m.c = splits * 32; m.vals_are_bad = 1;
-        m.largest = metric == PB200_METRIC_IP; m.k_pass = p.k_pass; m.k_total = k;
-        m.col_off = col; m.use_floor = 0;  // partial lists are already beyond the floor
-        m.out_scores = out_scores; m.out_ids = out_ids;
-        topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(m);
-        rc = check_launch("topk_merge_kernel");
-        if (rc) return rc;
-    }
-    return PB200_OK;
+    return topk_fp32_run(queries, nq, items, nx, dim, k, metric, qn, xn, exclude_ids, id_offset,
+                         out_scores, out_ids, part_bad, part_ids, splits, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int pb200_topk_merge(const float* scores, const int32_t* ids, int64_t nq, int c, int k,

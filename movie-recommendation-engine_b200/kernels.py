@@ -237,7 +237,16 @@ def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N
     return out
 
 
-def topk(queries, items, k, metric, exclude_ids=None, id_offset=0):
+# queries below this count stay on the fp32 kernel under precision="auto" (a 256-row query
+# group per CTA is mostly padding and the operand preparation is not amortised)
+TOPK_TC_MIN_QUERIES = 256
+
+
+def topk(queries, items, k, metric, exclude_ids=None, id_offset=0, precision="auto", stats=None):
+    """Exact top-k.  precision: "fp32" = CUDA-core kernel (pb200_topk); "tf32" = tensor-core
+    shortlist + exact fp32 re-rank + certificate (pb200_topk_tc, bitwise the same result);
+    "auto" = "tf32" where the shape is covered and the batch is large enough.  `stats`, if a
+    dict, receives {"path": ..., "fp32_reruns": device int32 tensor}."""
     dev = N.device_of(items, queries)
     q = N.dev_tensor(queries, torch.float32, dev)
     x = N.dev_tensor(items, torch.float32, dev)
@@ -247,13 +256,35 @@ def topk(queries, items, k, metric, exclude_ids=None, id_offset=0):
     nx = x.size(0)
     if x.size(1) != d:
         raise RuntimeError(f"dimension mismatch: queries {d}, items {x.size(1)}")
+    if precision not in ("auto", "fp32", "tf32"):
+        raise ValueError(f"precision must be 'auto', 'fp32' or 'tf32', got {precision!r}")
     ex = None if exclude_ids is None else N.dev_tensor(exclude_ids, torch.int32, dev)
     scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    use_tc = False
+    if precision != "fp32" and nq > 0:
+        ok = bool(lib().pb200_topk_tc_supported(nq, nx, d, k, 0 if ex is None else 1))
+        ok = ok and q.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0
+        if precision == "tf32" and not ok:
+            raise N.NativeError("topk: precision='tf32' needs dim % 4 == 0, dim <= 256, "
+                                f"k (+1 with exclude_ids) <= 24 (got dim={d}, k={k})")
+        use_tc = ok and (precision == "tf32" or nq >= TOPK_TC_MIN_QUERIES)
+    if use_tc:
+        ws_bytes = lib().pb200_topk_tc_workspace_bytes(nq, nx, d, k)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        reruns = torch.zeros(1, dtype=torch.int32, device=dev) if stats is not None else None
+        check(lib().pb200_topk_tc(ptr(q), nq, ptr(x), nx, d, k, metric, ptr(ex), int(id_offset),
+                                  ptr(scores), ptr(ids), ptr(ws), ws_bytes, ptr(reruns),
+                                  stream_ptr(dev)), "topk_tc")
+        if stats is not None:
+            stats.update(path="tf32", fp32_reruns=reruns)
+        return scores, ids
     ws_bytes = lib().pb200_topk_workspace_bytes(nq, nx, d, k)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     check(lib().pb200_topk(ptr(q), nq, ptr(x), nx, d, k, metric, ptr(ex), int(id_offset),
                            ptr(scores), ptr(ids), ptr(ws), ws_bytes, stream_ptr(dev)), "topk")
+    if stats is not None:
+        stats.update(path="fp32", fp32_reruns=None)
     return scores, ids
 
 

@@ -175,3 +175,68 @@ def test_benchmark_search_methods_dict(K):
         assert m["indices"].shape == (100, 10) and m["index_size"] == 3000
     assert res["ivf"]["recall"] > 0.8 and 0.0 <= res["lsh"]["recall"] <= 1.0
     assert (res["exact"]["indices"][:, 0] == np.arange(100)).all()
+
+
+# ---- tensor-core exact search (pb200_topk_tc): bitwise equal to the fp32 kernel -----------------
+def _tc_vs_fp32(K, q, x, k, metric, exclude=None, id_offset=0):
+    from mre_b200 import _native as N
+    m = N.METRIC_IP if metric == "ip" else N.METRIC_L2
+    qd, xd = torch.from_numpy(q).cuda(), torch.from_numpy(x).cuda()
+    ex = None if exclude is None else torch.from_numpy(exclude).cuda()
+    st = {}
+    s1, i1 = K.topk(qd, xd, k, m, exclude_ids=ex, id_offset=id_offset, precision="tf32", stats=st)
+    s0, i0 = K.topk(qd, xd, k, m, exclude_ids=ex, id_offset=id_offset, precision="fp32")
+    assert st["path"] == "tf32"
+    np.testing.assert_array_equal(i1.cpu().numpy(), i0.cpu().numpy())
+    np.testing.assert_array_equal(s1.cpu().numpy(), s0.cpu().numpy())
+    return int(st["fp32_reruns"].item())
+
+
+@pytest.mark.parametrize("nq,nx,d,k", [(300, 5000, 128, 10), (257, 1300, 64, 10), (1000, 9000, 128, 20),
+                                       (129, 700, 256, 10), (40, 128, 32, 5), (600, 100, 100, 12),
+                                       (256, 4096, 4, 3), (1, 3000, 128, 10), (513, 20000, 96, 24)])
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_exact_topk_tensor_core_bitwise_equals_fp32(K, nq, nx, d, k, metric):
+    x, q = _data(nx, d, 11), _data(nq, d, 12)
+    _tc_vs_fp32(K, q, x, k, metric)
+
+
+def test_exact_topk_tensor_core_self_queries_exclude_offset(K):
+    """All-item self queries (the E1 call pattern): exclude_ids drops the query itself, id_offset
+    shifts ids (item-sharded search); unnormalised vectors exercise the |q| max|x| bound."""
+    x = _data(7000, 128, 21, normalise=False) * 3.0
+    excl = np.arange(7000, dtype=np.int32) + 1000
+    reruns = _tc_vs_fp32(K, x, x, 10, "ip", exclude=excl, id_offset=1000)
+    assert reruns < 7000 // 4
+    _tc_vs_fp32(K, x, x, 10, "l2")
+
+
+def test_exact_topk_tensor_core_near_ties_fall_back_to_fp32(K):
+    """Collapsed embeddings (pairwise cosine ~0.985) put many scores within the
+    TF32 error bound: the certificate must fail and the fp32 re-run must still give the exact
+    result; duplicates exercise the id tie-break."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    base = rng.standard_normal((1, 64)).astype(np.float32)
+    x = base + 0.02 * rng.standard_normal((6000, 64)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    x[100:140] = x[99]                       # exact duplicates
+    reruns = _tc_vs_fp32(K, x[:700].copy(), x, 10, "ip")
+    assert reruns > 0
+    _tc_vs_fp32(K, x[:700].copy(), x, 10, "l2")
+
+
+def test_exact_topk_tensor_core_full_size_properties(K):
+    """C3-sized all-item search: too large for the numpy oracle, so check size-independent
+    properties -- every returned score is the fp32 score of the returned id, scores are sorted,
+    the query itself is rank 0 for L2, and a random sample of rows equals the fp32 kernel."""
+    from mre_b200 import _native as N
+    from mre_b200 import synthetic as S
+    x = S.spread_embeddings(62423, 128, seed=1).cuda().contiguous()
+    st = {}
+    s, i = K.topk(x, x, 10, N.METRIC_L2, precision="tf32", stats=st)
+    assert (i[:, 0] == torch.arange(62423, device="cuda", dtype=torch.int32)).float().mean() > 0.999
+    assert bool((s[:, 1:] >= s[:, :-1]).all())
+    rows = torch.randperm(62423, generator=torch.Generator().manual_seed(0))[:2048].cuda()
+    s0, i0 = K.topk(x[rows].contiguous(), x, 10, N.METRIC_L2, precision="fp32")
+    assert torch.equal(i[rows], i0) and torch.equal(s[rows], s0)
+    assert int(st["fp32_reruns"].item()) < 62423 // 10
