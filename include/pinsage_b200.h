@@ -233,6 +233,16 @@ int pb200_hamming_topk(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_
                        int code_bytes, int k, int32_t id_offset, float* out_dist,
                        int32_t* out_ids, pb200_stream_t stream);
 
+/* Same contract and the same results as pb200_hamming_topk on the tensor cores: codes expanded
+ * to +-1 bf16 vectors, <a,b> = nbits - 2 hamming(a,b) is exact in fp32, so the fused
+ * tcgen05 (kind::f16) GEMM + per-row shortlist kernel of pb200_topk_tc gives the exact top-k.
+ * code_bytes <= 64, k <= 32 (pb200_hamming_topk_tc_supported). */
+int pb200_hamming_topk_tc_supported(int64_t nq, int64_t nx, int code_bytes, int k);
+size_t pb200_hamming_topk_tc_workspace_bytes(int64_t nq, int64_t nx, int code_bytes, int k);
+int pb200_hamming_topk_tc(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x, int64_t nx,
+                          int code_bytes, int k, int32_t id_offset, float* out_dist, int32_t* out_ids,
+                          void* workspace, size_t workspace_bytes, pb200_stream_t stream);
+
 /* bucketed mode: num_tables keys of (8*code_bytes/num_tables) in {8,16} bits.
  * bucket_offsets int32 [num_tables, 2^key_bits + 1], bucket_ids int32 [num_tables, nx]. */
 size_t pb200_lsh_tables_workspace_bytes(int64_t nx, int code_bytes, int num_tables);

@@ -48,6 +48,7 @@ struct SearchParams {
     int ks;                          // shortlist length (16 or 32)
     int splits; int64_t split_len;   // item chunks per query group; chunk length (multiple of kTileN)
     int stages, align_slack;
+    int kind;                        // 0: tf32 operands (32 per 128 B chunk row), 1: bf16 (64 per chunk row)
     const float* __restrict__ hx;    // 0.5 |x|^2, padded to a multiple of 128 items (L2 only)
     unsigned long long* short_keys;  // [splits][nq][ks]   sorted, 0 = empty; slot = first chunk of a segment
 };
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
     if (warp == kProdWarp) {
         // ===================== TMA producer =====================
         int gc = 0, it = 0;
+        const int chunk_elems = p.kind == 1 ? 64 : kChunkK;
         for (int64_t t = t_begin; t < t_end; ++it) {
             const Seg sg = segment(t);
             t = sg.t_next;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
                 mbar_expect_tx(bar(kBarAFull), (uint32_t)(qt * nchunks) * kABytes);
                 for (int qi = 0; qi < qt; ++qi)
                     for (int c = 0; c < nchunks; ++c)
-                        tma_load_2d(a_base + (uint32_t)(qi * nchunks + c) * kABytes, &tm_q, c * kChunkK,
+                        tma_load_2d(a_base + (uint32_t)(qi * nchunks + c) * kABytes, &tm_q, c * chunk_elems,
                                     (int)(qg * rows_per_cta + qi * kTileM), bar(kBarAFull));
             }
             __syncwarp();
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
                     if (uu > 0) mbar_wait(bar(kBarEmpty + s), (uint32_t)((uu - 1) & 1));
                     if (lane == 0) {
                         mbar_expect_tx(bar(kBarFull + s), (uint32_t)kNBytes);
-                        tma_load_2d(b_base + (uint32_t)s * kNBytes, &tm_x, c * kChunkK,
+                        tma_load_2d(b_base + (uint32_t)s * kNBytes, &tm_x, c * chunk_elems,
                                     (int)(n_begin + (int64_t)nt * kTileN), bar(kBarFull + s));
                     }
                     __syncwarp();
@@ -200,7 +202,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         // D=F32, A=B=TF32, K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+        // (kind::f16 with bf16 operands: format code 1 instead of 2)
+        const uint32_t fmt = p.kind == 1 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                                ((uint32_t)(kTileM >> 4) << 24);
         int gc = 0, it = 0, tc_ = 0;
         for (int64_t t = t_begin; t < t_end; ++it) {
@@ -221,10 +225,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
                         for (int qi = 0; qi < qt; ++qi) {
                             const uint32_t a_s = a_base + (uint32_t)(qi * nchunks + c) * kABytes;
                             const uint32_t tmem_d = tmem_base + (uint32_t)((b * qt + qi) * kTileN);
+                            if (p.kind == 1) {
 #pragma unroll
-                            for (int k = 0; k < kChunkK / 8; ++k)
-                                mma_tf32(tmem_d, make_desc(a_s + k * 32), make_desc(b_s + k * 32), idesc,
-                                         (uint32_t)((c | k) != 0));
+                                for (int k = 0; k < 4; ++k)   // 4 x K=16 bf16 = one 128-byte chunk row
+                                    mma_bf16(tmem_d, make_desc(a_s + k * 32), make_desc(b_s + k * 32), idesc,
+                                             (uint32_t)((c | k) != 0));
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < kChunkK / 8; ++k)
+                                    mma_tf32(tmem_d, make_desc(a_s + k * 32), make_desc(b_s + k * 32), idesc,
+                                             (uint32_t)((c | k) != 0));
+                            }
                         }
                         mma_commit(bar(kBarEmpty + s));
                         if (c == nchunks - 1) mma_commit(bar(kBarTFull + b));
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
 
 // ---- host side ----
 struct Plan {
-    int qt, nchunks, ks, splits, stages, grid, fsplits, fsplits0, ctas_per_sm, align_slack;
+    int qt = 0, nchunks = 0, ks = 0, splits = 0, stages = 0, grid = 0, fsplits = 0, fsplits0 = 0, ctas_per_sm = 1, align_slack = 1024;
     int64_t split_len, nx_pad, cap_f, cap_f0;
     size_t smem_bytes;
     // workspace offsets
@@ -464,20 +475,11 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-static bool make_plan(int64_t nq, int64_t nx, int dim, int k, bool has_exclude, Plan* pl) {
-    if (dim % 4 || dim > 256 || dim <= 0 || nq <= 0 || nx <= 0) return false;
-    const int need = k + (has_exclude ? 1 : 0);
-    if (need > 24) return false;
-    Plan p{};
-    p.ks = need <= 12 ? 16 : 32;
-    const int ks_env = env_int("PB200_TOPK_TC_KS", 0);
-    if (ks_env == 16 || ks_env == 32) { if (ks_env >= need) p.ks = ks_env; }
-    p.nchunks = (dim + kChunkK - 1) / kChunkK;
-    // two resident query tiles per CTA halve the L2 -> SM item traffic; needs room for the
-    // operands, the sorted lists and >= 3 ring stages in 225 KB
+// kernel geometry for nq x nx scores with `nchunks` 128-byte K chunks per row and lists of p.ks
+static bool make_geometry(int64_t nq, int64_t nx, Plan& p) {
     // Two configurations (PB200_TOPK_TC_CTAS): 1 CTA/SM with two resident query tiles (halves the
-    // L2 -> SM item traffic), or 2 CTAs/SM with one tile each (twice the scan warps per SM to hide
-    // the shuffle / shared-memory latency of the list insertions).
+    // L2 -> SM item traffic; default), or 2 CTAs/SM with one tile each (twice the scan warps per
+    // SM; measured slower: 4.99 vs 4.28 ms at C3).
     p.ctas_per_sm = env_int("PB200_TOPK_TC_CTAS", 1) == 2 ? 2 : 1;
     p.align_slack = 1024;
     auto fixed_bytes = [&](int qt) {
@@ -508,6 +510,19 @@ static bool make_plan(int64_t nq, int64_t nx, int dim, int k, bool has_exclude, 
     p.splits = (int)ceil_div(nx, p.split_len);          // no empty chunk
     const int64_t total_sub = qgroups * p.splits;
     p.grid = (int)(total_sub < kSMs * p.ctas_per_sm ? total_sub : kSMs * p.ctas_per_sm);
+    return true;
+}
+
+static bool make_plan(int64_t nq, int64_t nx, int dim, int k, bool has_exclude, Plan* pl) {
+    if (dim % 4 || dim > 256 || dim <= 0 || nq <= 0 || nx <= 0) return false;
+    const int need = k + (has_exclude ? 1 : 0);
+    if (need > 24) return false;
+    Plan p{};
+    p.ks = need <= 12 ? 16 : 32;
+    const int ks_env = env_int("PB200_TOPK_TC_KS", 0);
+    if (ks_env == 16 || ks_env == 32) { if (ks_env >= need) p.ks = ks_env; }
+    p.nchunks = (dim + kChunkK - 1) / kChunkK;
+    if (!make_geometry(nq, nx, p)) return false;
     p.nx_pad = ceil_div(nx, kTileN) * kTileN + kTileN;
     // fp32 re-runs: a first round for up to 1,024 uncertified queries with many item splits (the
     // usual case is a handful of queries: latency of one block chain), then nq/4 per round
@@ -612,7 +627,7 @@ extern "C" int pb200_topk_tc(const float* queries, int64_t nq, const float* item
     }
     tcs::SearchParams sp{};
     sp.nq = nq; sp.nx = nx; sp.d = dim; sp.nchunks = pl.nchunks; sp.qt = pl.qt; sp.ks = pl.ks;
-    sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack;
+    sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack; sp.kind = 0;
     sp.hx = hx;
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + pl.off_short);
     // slots no segment starts at stay empty (0)
@@ -657,4 +672,156 @@ extern "C" int pb200_topk_tc(const float* queries, int64_t nq, const float* item
     if (stats_out)   // [0] = number of queries re-run in fp32 (device-side counter, copied in stream order)
         PB_CUDA(cudaMemcpyAsync(stats_out, qsel_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     return PB200_OK;
+}
+
+
+// =====================================================================================
+// Exhaustive Hamming top-k (LSHIndex.search, utils/nearest_neighbors.py:47-68; what
+// faiss.IndexLSH computes) on the tensor cores: codes expanded to +-1 bf16 vectors,
+// <a, b> = nbits - 2 hamming(a, b) -- an exact small integer in fp32 -- so the same fused
+// GEMM + shortlist kernel (kind::f16, bf16 operands) yields the exact top-k: no re-rank, no
+// certificate.  Order: (distance asc, id asc) = pb200_hamming_topk.
+// =====================================================================================
+namespace pb200 {
+namespace tcs {
+
+__global__ void expand_codes_kernel(const uint8_t* __restrict__ codes, int64_t nbytes, uint4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = codes[i];   // bit j (LSB first) -> element 8 i + j: 1 -> +1.0, 0 -> -1.0 (bf16)
+        uint4 o;
+        o.x = ((b & 1u) ? 0x3F80u : 0xBF80u) | (((b & 2u) ? 0x3F80u : 0xBF80u) << 16);
+        o.y = ((b & 4u) ? 0x3F80u : 0xBF80u) | (((b & 8u) ? 0x3F80u : 0xBF80u) << 16);
+        o.z = ((b & 16u) ? 0x3F80u : 0xBF80u) | (((b & 32u) ? 0x3F80u : 0xBF80u) << 16);
+        o.w = ((b & 64u) ? 0x3F80u : 0xBF80u) | (((b & 128u) ? 0x3F80u : 0xBF80u) << 16);
+        out[i] = o;
+    }
+}
+
+// warp per query: merge the per-segment lists (already exact) -> distances + ids
+__global__ void __launch_bounds__(256) hamming_finish_kernel(const unsigned long long* __restrict__ short_keys,
+                                                             int64_t nq, int splits, int ks, int k, int nbits,
+                                                             int32_t id_offset, float* __restrict__ out_dist,
+                                                             int32_t* __restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    TopkLane best; best.bad = INFINITY; best.id = INT_MAX;
+    const int nc = splits * ks;
+    for (int base = 0; base < nc; base += 32) {
+        const int j = base + lane;
+        unsigned long long key = 0ull;
+        if (j < nc) key = short_keys[((size_t)(j / ks) * nq + q) * ks + (j % ks)];
+        const bool valid = key != 0ull;
+        const float dot = ord2f((uint32_t)(key >> 32));
+        const float dist = 0.5f * ((float)nbits - dot);          // exact: both are small integers
+        const int gid = (int)(0xFFFFFFFFu - (uint32_t)key) + id_offset;
+        topk_offer(best, dist, gid, valid, k, lane);
+    }
+    if (lane < k) {
+        const bool has = best.id != INT_MAX;
+        out_ids[q * k + lane] = has ? best.id : -1;
+        out_dist[q * k + lane] = has ? best.bad : INFINITY;
+    }
+}
+
+struct HPlan { Plan g; size_t off_q, off_x, off_short, total; bool shared; };
+
+static bool make_hplan(int64_t nq, int64_t nx, int code_bytes, int k, bool shared, HPlan* hp) {
+    const int nbits = code_bytes * 8;
+    if (code_bytes <= 0 || nbits > 512 || k <= 0 || k > 32 || nq <= 0 || nx <= 0) return false;
+    HPlan h{};
+    h.g.ks = k <= 16 ? 16 : 32;
+    h.g.nchunks = (nbits + 63) / 64;
+    if (!make_geometry(nq, nx, h.g)) return false;
+    h.shared = shared;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t r = off; off += align_up(bytes, 256); return r; };
+    h.off_x = take((size_t)nx * nbits * 2);
+    h.off_q = shared ? h.off_x : take((size_t)nq * nbits * 2);
+    h.off_short = take((size_t)h.g.splits * nq * h.g.ks * 8);
+    h.total = off;
+    *hp = h;
+    return true;
+}
+
+}  // namespace tcs
+}  // namespace pb200
+
+extern "C" int pb200_hamming_topk_tc_supported(int64_t nq, int64_t nx, int code_bytes, int k) {
+    tcs::HPlan h;
+    return tcs::make_hplan(nq, nx, code_bytes, k, false, &h) ? 1 : 0;
+}
+
+extern "C" size_t pb200_hamming_topk_tc_workspace_bytes(int64_t nq, int64_t nx, int code_bytes, int k) {
+    tcs::HPlan h;
+    return tcs::make_hplan(nq, nx, code_bytes, k, false, &h) ? h.total : 0;
+}
+
+extern "C" int pb200_hamming_topk_tc(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x, int64_t nx,
+                                     int code_bytes, int k, int32_t id_offset, float* out_dist,
+                                     int32_t* out_ids, void* workspace, size_t workspace_bytes,
+                                     pb200_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PB_REQUIRE(nq >= 0 && nx >= 0 && code_bytes > 0 && k > 0, "hamming_topk_tc: bad sizes");
+    PB_REQUIRE(nx + (int64_t)id_offset < 2147483647ll, "hamming_topk_tc: ids overflow int32");
+    if (nq == 0) return PB200_OK;
+    const bool shared = codes_q == codes_x && nq == nx;
+    tcs::HPlan h;
+    if (!tcs::make_hplan(nq, nx, code_bytes, k, shared, &h)) {
+        set_error("hamming_topk_tc: needs code_bytes <= 64, k <= 32, nx > 0 (got code_bytes=%d k=%d nx=%lld)",
+                  code_bytes, k, (long long)nx);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    PB_REQUIRE(codes_q && codes_x && out_dist && out_ids && workspace, "hamming_topk_tc: null pointer");
+    PB_REQUIRE((uintptr_t)workspace % 16 == 0, "hamming_topk_tc: workspace must be 16-byte aligned");
+    if (workspace_bytes < h.total) {
+        set_error("hamming_topk_tc: workspace %zu B < required %zu B", workspace_bytes, h.total);
+        return PB200_ERR_WORKSPACE;
+    }
+    const int nbits = code_bytes * 8;
+    char* ws = static_cast<char*>(workspace);
+    void* xb = ws + h.off_x;
+    void* qb = ws + h.off_q;
+    {
+        const int64_t nb = nx * code_bytes;
+        const int64_t blocks = ceil_div(nb, 256) < kSMs * 8 ? ceil_div(nb, 256) : kSMs * 8;
+        tcs::expand_codes_kernel<<<(unsigned)blocks, 256, 0, stream>>>(codes_x, nb, static_cast<uint4*>(xb));
+        int rc = check_launch("expand_codes_kernel");
+        if (rc) return rc;
+        if (!shared) {
+            const int64_t nbq = nq * code_bytes;
+            const int64_t bq = ceil_div(nbq, 256) < kSMs * 8 ? ceil_div(nbq, 256) : kSMs * 8;
+            tcs::expand_codes_kernel<<<(unsigned)bq, 256, 0, stream>>>(codes_q, nbq, static_cast<uint4*>(qb));
+            rc = check_launch("expand_codes_kernel");
+            if (rc) return rc;
+        }
+    }
+    alignas(64) CUtensorMap tm_q, tm_x;
+    if (!make_map_bf16(&tm_q, qb, nq, nbits, tc::kTileM) || !make_map_bf16(&tm_x, xb, nx, nbits, tcs::kTileN)) {
+        set_error("hamming_topk_tc: cuTensorMapEncodeTiled failed (nq=%lld nx=%lld bits=%d)", (long long)nq,
+                  (long long)nx, nbits);
+        return PB200_ERR_CUDA;
+    }
+    const tcs::Plan& pl = h.g;
+    tcs::SearchParams sp{};
+    sp.nq = nq; sp.nx = nx; sp.d = nbits; sp.nchunks = pl.nchunks; sp.qt = pl.qt; sp.ks = pl.ks;
+    sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack;
+    sp.kind = 1; sp.hx = nullptr;
+    sp.short_keys = reinterpret_cast<unsigned long long*>(ws + h.off_short);
+    PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
+    if (pl.ctas_per_sm == 2) {
+        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_IP, 2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        tcs::search_tc_kernel<PB200_METRIC_IP, 2><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
+    } else {
+        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_IP, 1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        tcs::search_tc_kernel<PB200_METRIC_IP, 1><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
+    }
+    int rc = check_launch("search_tc_kernel");
+    if (rc) return rc;
+    tcs::hamming_finish_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(
+        sp.short_keys, nq, pl.splits, pl.ks, k, nbits, id_offset, out_dist, out_ids);
+    return check_launch("hamming_finish_kernel");
 }

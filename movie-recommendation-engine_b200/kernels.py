@@ -313,12 +313,31 @@ def lsh_encode(x, proj, return_projection=False):
     return (codes, y) if return_projection else codes
 
 
-def hamming_topk(codes_q, codes_x, k, id_offset=0):
+def hamming_topk(codes_q, codes_x, k, id_offset=0, precision="auto"):
+    """Exhaustive Hamming top-k.  precision: "simt" = xor + popcount kernel (pb200_hamming_topk);
+    "tc" = +-1 bf16 GEMM on the tensor cores fused with the shortlist (pb200_hamming_topk_tc, exact:
+    same distances and ids); "auto" = "tc" where covered and the query batch is large enough."""
     dev = N.device_of(codes_x)
     nq, cb = codes_q.shape
+    nx = codes_x.size(0)
+    if precision not in ("auto", "simt", "tc"):
+        raise ValueError(f"precision must be 'auto', 'simt' or 'tc', got {precision!r}")
     dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    check(lib().pb200_hamming_topk(ptr(codes_q), nq, ptr(codes_x), codes_x.size(0), cb, k,
+    use_tc = False
+    if precision != "simt" and nq > 0:
+        ok = bool(lib().pb200_hamming_topk_tc_supported(nq, nx, cb, k))
+        if precision == "tc" and not ok:
+            raise N.NativeError(f"hamming_topk: precision='tc' needs code_bytes <= 64, k <= 32 (got {cb}, {k})")
+        use_tc = ok and (precision == "tc" or nq >= TOPK_TC_MIN_QUERIES)
+    if use_tc:
+        ws_bytes = lib().pb200_hamming_topk_tc_workspace_bytes(nq, nx, cb, k)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        check(lib().pb200_hamming_topk_tc(ptr(codes_q), nq, ptr(codes_x), nx, cb, k, int(id_offset),
+                                          ptr(dist), ptr(ids), ptr(ws), ws_bytes, stream_ptr(dev)),
+              "hamming_topk_tc")
+        return dist, ids
+    check(lib().pb200_hamming_topk(ptr(codes_q), nq, ptr(codes_x), nx, cb, k,
                                    int(id_offset), ptr(dist), ptr(ids), stream_ptr(dev)),
           "hamming_topk")
     return dist, ids

@@ -240,3 +240,22 @@ def test_exact_topk_tensor_core_full_size_properties(K):
     s0, i0 = K.topk(x[rows].contiguous(), x, 10, N.METRIC_L2, precision="fp32")
     assert torch.equal(i[rows], i0) and torch.equal(s[rows], s0)
     assert int(st["fp32_reruns"].item()) < 62423 // 10
+
+
+# ---- tensor-core exhaustive Hamming search (pb200_hamming_topk_tc): equal to the popcount kernel ----
+@pytest.mark.parametrize("nq,nx,code_bytes,k", [(300, 5000, 32, 10), (1, 700, 32, 10), (513, 20000, 32, 32),
+                                                (260, 999, 4, 5), (1000, 3000, 64, 16), (300, 40, 16, 10),
+                                                (257, 4097, 8, 17)])
+def test_hamming_topk_tensor_core_equals_popcount_kernel(K, nq, nx, code_bytes, k):
+    rng = np.random.Generator(np.random.PCG64(nq + nx))
+    cx = torch.from_numpy(rng.integers(0, 256, (nx, code_bytes), dtype=np.uint8)).cuda()
+    cq = torch.from_numpy(rng.integers(0, 256, (nq, code_bytes), dtype=np.uint8)).cuda()
+    cq[: min(nq, nx) // 2] = cx[: min(nq, nx) // 2]          # exact matches and many ties
+    d1, i1 = K.hamming_topk(cq, cx, k, id_offset=7, precision="tc")
+    d0, i0 = K.hamming_topk(cq, cx, k, id_offset=7, precision="simt")
+    np.testing.assert_array_equal(d1.cpu().numpy(), d0.cpu().numpy())
+    np.testing.assert_array_equal(i1.cpu().numpy(), i0.cpu().numpy())
+    # self search (shared expansion of the codes)
+    d1, i1 = K.hamming_topk(cx, cx, min(k, 16), precision="tc")
+    d0, i0 = K.hamming_topk(cx, cx, min(k, 16), precision="simt")
+    assert torch.equal(d1, d0) and torch.equal(i1, i0)
