@@ -144,6 +144,27 @@ int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
                const float* weights, const int32_t* list_len, const int32_t* weight_len,
                int64_t n, int max_neighbors, int mode, float* out, pb200_stream_t stream);
 
+/* Multi-GPU form of pb200_pool: x is split in contiguous row shards of shard_rows rows, shard r
+ * living in rank r's memory (shard_ptrs[r]: a device pointer valid in THIS process -- the
+ * rank's own buffer or a peer buffer opened with pb200_peer_open).  Neighbour rows are read
+ * from their owners over NVLink peer access; this replaces the per-layer all-gather of h
+ *  by ~1.3 remote rows per node.  shard_ptrs is a HOST array of `world` pointers. */
+#define PB200_MAX_PEERS 16
+int pb200_pool_sharded(const float* const* shard_ptrs, int world, int64_t shard_rows, int64_t num_rows,
+                       int dim, const int32_t* ids, const float* weights, const int32_t* list_len,
+                       const int32_t* weight_len, int64_t n, int max_neighbors, int mode, float* out,
+                       pb200_stream_t stream);
+
+/* Exchange buffers for pb200_pool_sharded: plain cudaMalloc allocations exported / opened
+ * through CUDA IPC (one process per GPU on one box).  Handles are opaque 64-byte blobs that the
+ * host side passes between ranks (torch.distributed all_gather_object). */
+#define PB200_PEER_HANDLE_BYTES 64
+int pb200_peer_alloc(size_t bytes, void** ptr_out);
+int pb200_peer_free(void* ptr);
+int pb200_peer_export(const void* ptr, uint8_t handle_out[PB200_PEER_HANDLE_BYTES]);
+int pb200_peer_open(const uint8_t handle[PB200_PEER_HANDLE_BYTES], void** ptr_out);
+int pb200_peer_close(void* ptr);
+
 /* ------------------------------------------------------------------------------------
  * G1-G3  fused [gather -> importance sum -> concat -> dense -> epilogue]
  *   out[m,:] = epi( [A1[m,:K1] | A2row(m)] . W^T + bias )          out: float32 [n, N]

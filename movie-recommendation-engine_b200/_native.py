@@ -40,6 +40,13 @@ SIGNATURES = {
     "pb200_count_topt": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pb200_pool": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int,
                            c_ptr, c_ptr]),
+    "pb200_pool_sharded": (c_int, [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                                   c_int, c_int, c_ptr, c_ptr]),
+    "pb200_peer_alloc": (c_int, [c_size, c_ptr]),
+    "pb200_peer_free": (c_int, [c_ptr]),
+    "pb200_peer_export": (c_int, [c_ptr, c_ptr]),
+    "pb200_peer_open": (c_int, [c_ptr, c_ptr]),
+    "pb200_peer_close": (c_int, [c_ptr]),
     "pb200_gather_dense": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
                                    c_int, c_int, c_ptr, c_ptr]),

@@ -6,6 +6,8 @@
 // One warp per output row; neighbour rows are read as coalesced 16-byte vectors
 // (a 256-float row = two 512 B warp requests).  HBM/L2-bandwidth bound:
 // 4*dim*(valid+1) + 8*T bytes per row.
+#include <cstring>
+
 #include "pool.cuh"
 
 namespace pb200 {
@@ -16,10 +18,20 @@ __device__ __forceinline__ float round_tf32(float f) {
     return __uint_as_float(r);
 }
 
+// Row-sharded x (multi-GPU): rows [r * shard_rows, (r+1) * shard_rows) live in rank r's memory,
+// mapped into this process by CUDA IPC; a neighbour row is read straight from its owner over
+// NVLink (16-byte vector loads, ~1.3 valid rows per node on the bipartite graph) instead of
+// all-gathering the whole h matrix every layer.  world == 0: plain single-buffer x.
+struct PeerMap {
+    const float* base[PB200_MAX_PEERS];
+    int64_t shard_rows;
+    int world;
+};
+
 template <bool kVec>
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int dim,
                                                    ListArgs a, int64_t n, float* __restrict__ out,
-                                                   bool round_out) {
+                                                   bool round_out, const PeerMap pm) {
     extern __shared__ int32_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -36,7 +48,14 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
                 for (int r = 0; r < nv; ++r) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)s_id[r] * dim + c));
+                    const float* xr;
+                    if (pm.world > 0) {
+                        const int owner = (int)(s_id[r] / pm.shard_rows);
+                        xr = pm.base[owner] + ((int64_t)s_id[r] - owner * pm.shard_rows) * dim;
+                    } else {
+                        xr = x + (int64_t)s_id[r] * dim;
+                    }
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
                     if (is_max) {
                         acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
                         acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
@@ -56,7 +75,14 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
             for (int c = lane; c < dim; c += 32) {
                 float acc = is_max && nv ? -INFINITY : 0.f;
                 for (int r = 0; r < nv; ++r) {
-                    const float v = __ldg(x + (int64_t)s_id[r] * dim + c);
+                    const float* xr;
+                    if (pm.world > 0) {
+                        const int owner = (int)(s_id[r] / pm.shard_rows);
+                        xr = pm.base[owner] + ((int64_t)s_id[r] - owner * pm.shard_rows) * dim;
+                    } else {
+                        xr = x + (int64_t)s_id[r] * dim;
+                    }
+                    const float v = __ldg(xr + c);
                     acc = is_max ? fmaxf(acc, v) : fmaf(s_w[r], v, acc);
                 }
                 o[c] = round_out ? round_tf32(acc) : acc;
@@ -70,27 +96,83 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
 
 using namespace pb200;
 
-extern "C" int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
-                          const float* weights, const int32_t* list_len,
-                          const int32_t* weight_len, int64_t n, int max_neighbors, int mode,
-                          float* out, pb200_stream_t stream) {
+static int pool_launch(const float* x, const PeerMap& pm, int64_t num_rows, int dim, const int32_t* ids,
+                       const float* weights, const int32_t* list_len, const int32_t* weight_len,
+                       int64_t n, int max_neighbors, int mode, float* out, cudaStream_t stream) {
     PB_REQUIRE(n >= 0 && dim > 0 && max_neighbors > 0 && num_rows >= 0, "pool: bad sizes");
     const bool round_out = mode & PB200_POOL_ROUND_TF32;
     mode &= ~PB200_POOL_ROUND_TF32;
     PB_REQUIRE(mode >= PB200_POOL_PINSAGE && mode <= PB200_POOL_MAX, "pool: unknown mode %d", mode);
     if (n == 0) return PB200_OK;
-    PB_REQUIRE(x && ids && out, "pool: null pointer");
+    PB_REQUIRE((x || pm.world > 0) && ids && out, "pool: null pointer");
     ListArgs a{ids, weights, list_len, weight_len, max_neighbors, mode, num_rows};
     const int wpb = 8;
     const size_t smem = (size_t)wpb * 2 * max_neighbors * sizeof(int32_t);
     PB_REQUIRE(smem <= 200 * 1024, "pool: max_neighbors=%d too large", max_neighbors);
-    const bool vec = dim % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    bool vec = dim % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    for (int r = 0; r < pm.world; ++r) vec = vec && ((uintptr_t)pm.base[r] % 16 == 0);
     auto kern = vec ? pool_kernel<true> : pool_kernel<false>;
     if (smem > 48 * 1024)
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(n, wpb);
     const int64_t cap = (int64_t)kSMs * 16;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(x, dim, a, n, out, round_out);
+    kern<<<(unsigned)blocks, wpb * 32, smem, stream>>>(x, dim, a, n, out, round_out, pm);
     return check_launch("pool_kernel");
+}
+
+extern "C" int pb200_pool(const float* x, int64_t num_rows, int dim, const int32_t* ids,
+                          const float* weights, const int32_t* list_len,
+                          const int32_t* weight_len, int64_t n, int max_neighbors, int mode,
+                          float* out, pb200_stream_t stream) {
+    PeerMap pm{};
+    return pool_launch(x, pm, num_rows, dim, ids, weights, list_len, weight_len, n, max_neighbors, mode,
+                       out, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_pool_sharded(const float* const* shard_ptrs, int world, int64_t shard_rows,
+                                  int64_t num_rows, int dim, const int32_t* ids, const float* weights,
+                                  const int32_t* list_len, const int32_t* weight_len, int64_t n,
+                                  int max_neighbors, int mode, float* out, pb200_stream_t stream) {
+    PB_REQUIRE(shard_ptrs && world >= 1 && world <= PB200_MAX_PEERS && shard_rows > 0,
+               "pool_sharded: need 1..%d shard pointers and shard_rows > 0", PB200_MAX_PEERS);
+    PB_REQUIRE(num_rows <= (int64_t)world * shard_rows, "pool_sharded: num_rows exceeds world * shard_rows");
+    PeerMap pm{};
+    for (int r = 0; r < world; ++r) {
+        PB_REQUIRE(shard_ptrs[r], "pool_sharded: shard pointer %d is null", r);
+        pm.base[r] = shard_ptrs[r];
+    }
+    pm.shard_rows = shard_rows; pm.world = world;
+    return pool_launch(nullptr, pm, num_rows, dim, ids, weights, list_len, weight_len, n, max_neighbors,
+                       mode, out, (cudaStream_t)stream);
+}
+
+// ---- peer buffers: cudaMalloc'ed exchange buffers shared between the ranks of one box by CUDA IPC ----
+extern "C" int pb200_peer_alloc(size_t bytes, void** ptr_out) {
+    PB_REQUIRE(ptr_out && bytes > 0, "peer_alloc: bad arguments");
+    PB_CUDA(cudaMalloc(ptr_out, bytes));
+    return PB200_OK;
+}
+extern "C" int pb200_peer_free(void* ptr) {
+    if (ptr) PB_CUDA(cudaFree(ptr));
+    return PB200_OK;
+}
+extern "C" int pb200_peer_export(const void* ptr, uint8_t handle_out[PB200_PEER_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == PB200_PEER_HANDLE_BYTES, "IPC handle size");
+    PB_REQUIRE(ptr && handle_out, "peer_export: null pointer");
+    cudaIpcMemHandle_t h;
+    PB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+    memcpy(handle_out, &h, sizeof(h));
+    return PB200_OK;
+}
+extern "C" int pb200_peer_open(const uint8_t handle[PB200_PEER_HANDLE_BYTES], void** ptr_out) {
+    PB_REQUIRE(handle && ptr_out, "peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    PB_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PB200_OK;
+}
+extern "C" int pb200_peer_close(void* ptr) {
+    if (ptr) PB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return PB200_OK;
 }

@@ -4,7 +4,11 @@ What shards and what is exchanged:
   * walks       start nodes are split in contiguous blocks; the CSR is replicated; no
                 collective (Philox counters make a node's sample independent of its shard).
   * conv layers rows are split the same way; layer l+1 gathers rows of h^(l) from arbitrary
-                nodes, so each layer ends with ONE all-gather of the row shards of h.
+                nodes.  On GPUs of one box the pooling kernel reads those rows straight from
+                their owner's memory over NVLink (CUDA IPC peer buffers, `PeerBuffers`; ~1.3
+                remote rows per node instead of the whole matrix) and the only collective is a
+                one-element all-reduce per layer as a stream-ordered barrier.  The all-gather
+                of the row shards of h is kept for CPU/gloo runs and the exact-fp32 path.
   * search      queries are split, the index is replicated, results are all-gathered; or items
                 are split (exact search on catalogues that do not fit one GPU), every rank
                 returns a local top-k with global ids, and the all-gathered lists are merged
@@ -61,6 +65,105 @@ def all_gather_cols(local, group=None):
     return out.view(ws, nq, c).permute(1, 0, 2).reshape(nq, ws * c).contiguous()
 
 
+class _RawCuda:
+    """A cudaMalloc'ed region viewed through __cuda_array_interface__ (float32, C order)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerBuffers:
+    """`count` row-shard buffers [shard_rows, width] fp32 on every rank, allocated by
+    pb200_peer_alloc and opened on all peers with CUDA IPC (one process per GPU, one box).
+    `ptr_array(b)` is the host array of world pointers pb200_pool_sharded takes for buffer b;
+    `local(b)` is this rank's shard as a tensor.  `barrier()` is stream ordered."""
+
+    def __init__(self, count, shard_rows, width, dev, group=None):
+        import ctypes
+        from . import _native as N
+        self.group, self.dev = group, dev
+        self.rank, self.ws = world(group)
+        self.shard_rows, self.width, self.count = shard_rows, width, count
+        lib = N.lib()
+        nbytes = max(shard_rows * width * 4, 16)
+        self._own, handles = [], []
+        for _ in range(count):
+            p = ctypes.c_void_p()
+            N.check(lib.pb200_peer_alloc(nbytes, ctypes.byref(p)), "peer_alloc")
+            h = (ctypes.c_uint8 * 64)()
+            N.check(lib.pb200_peer_export(p, h), "peer_export")
+            self._own.append(p)
+            handles.append(bytes(h))
+        gathered = [None] * self.ws
+        dist.all_gather_object(gathered, handles, group=group)
+        self._opened, self._arrays, self._keep, self._local = [], [], [], []
+        for b in range(count):
+            ptrs = []
+            for r in range(self.ws):
+                if r == self.rank:
+                    ptrs.append(self._own[b].value)
+                else:
+                    q = ctypes.c_void_p()
+                    hb = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[r][b])
+                    N.check(lib.pb200_peer_open(hb, ctypes.byref(q)), "peer_open")
+                    self._opened.append(q)
+                    ptrs.append(q.value)
+            self._arrays.append((ctypes.c_void_p * self.ws)(*ptrs))
+            raw = _RawCuda(self._own[b].value, (shard_rows, width))
+            self._keep.append(raw)
+            self._local.append(torch.as_tensor(raw, device=dev))
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.barrier()
+
+    def ptr_array(self, b):
+        return self._arrays[b]
+
+    def local(self, b):
+        return self._local[b]
+
+    def barrier(self):
+        """All ranks' work queued before this point is complete before anything queued after it
+        starts on any rank (a one-element all-reduce on the compute stream)."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        from . import _native as N
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.group)
+        for q in self._opened:
+            N.lib().pb200_peer_close(q)
+        for p in self._own:
+            N.lib().pb200_peer_free(p)
+        self._opened, self._own, self._local, self._keep = [], [], [], []
+
+
+_PEER_CACHE = {}
+
+
+def peer_buffers(count, shard_rows, width, dev, group=None):
+    key = (count, shard_rows, width, str(dev), id(group))
+    if key not in _PEER_CACHE:
+        _PEER_CACHE[key] = PeerBuffers(count, shard_rows, width, dev, group)
+    return _PEER_CACHE[key]
+
+
+def release_peer_buffers():
+    for pb in _PEER_CACHE.values():
+        pb.close()
+    _PEER_CACHE.clear()
+
+
+def _use_peer_exchange(model, dev, ws):
+    import os
+    from . import _native as N
+    if ws == 1 or dev.type != "cuda" or ws > 16:
+        return False
+    if os.environ.get("PB200_SHARD_EXCHANGE", "p2p") != "p2p":
+        return False
+    return dist.get_backend() == "nccl" and model.precision != N.PREC_FP32 and not model.fuse_pool
+
+
 def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None):
     """PinSage.get_embeddings with rows split across ranks.  x_local: this rank's rows of the
     feature matrix (shard_range layout).  Returns this rank's rows of the embeddings."""
@@ -80,6 +183,27 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward
     PRE = 0 if model.precision == N.PREC_FP32 else N.IN_A1_TF32
     h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
+    if _use_peer_exchange(model, dev, ws):
+        # neighbour rows are read from their owners' memory; no all-gather
+        srows = shard_size(num_items, ws)
+        pb = peer_buffers(model.num_layers, srows, h_loc.size(1), dev, group)
+        for i in range(model.num_layers):
+            mine = pb.local(i)[:hi - lo]
+            mine.copy_(h_loc)
+            pb.barrier()                                        # every rank's h^(i) is in place
+            wf, bf = model._folded_layer(i)
+            ids, wts, ll, wl = batches[i].as_args()
+            h_neigh = K.pool_sharded(pb.ptr_array(i), ws, srows, num_items, h_loc.size(1), ids, wts, ll, wl,
+                                     N.POOL_PINSAGE | N.POOL_ROUND_TF32, dev)
+            h_loc = K.gather_dense(mine, wf, bf, a2=h_neigh,
+                                   flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
+                                   precision=model.precision)
+        # Buffer i is rewritten by the next call only after the barrier of layer i+1 (which every
+        # rank reaches after its pooling of layer i); a single layer has no such barrier.
+        if model.num_layers == 1:
+            pb.barrier()
+        return K.gather_dense(h_loc, *P(model.output_proj), flags=N.EPI_L2NORM | PRE,
+                              precision=model.precision)
     for i in range(model.num_layers):
         h_full = all_gather_rows(h_loc, num_items, group)   # the one exchange per layer
         wf, bf = model._folded_layer(i)
