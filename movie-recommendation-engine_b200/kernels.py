@@ -248,9 +248,11 @@ def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N
     return out
 
 
-# queries below this count stay on the fp32 kernel under precision="auto" (a 256-row query
-# group per CTA is mostly padding and the operand preparation is not amortised)
+# under precision="auto" small problems stay on the CUDA-core kernels: a 256-row query group per
+# CTA would be mostly padding, and the operand preparation / re-rank passes are not amortised
+# over a handful of items (e.g. the IVF coarse quantiser: 100 centroids)
 TOPK_TC_MIN_QUERIES = 256
+TOPK_TC_MIN_ITEMS = 2048
 
 
 def topk(queries, items, k, metric, exclude_ids=None, id_offset=0, precision="auto", stats=None):
@@ -279,7 +281,7 @@ def topk(queries, items, k, metric, exclude_ids=None, id_offset=0, precision="au
         if precision == "tf32" and not ok:
             raise N.NativeError("topk: precision='tf32' needs dim % 4 == 0, dim <= 256, "
                                 f"k (+1 with exclude_ids) <= 24 (got dim={d}, k={k})")
-        use_tc = ok and (precision == "tf32" or nq >= TOPK_TC_MIN_QUERIES)
+        use_tc = ok and (precision == "tf32" or (nq >= TOPK_TC_MIN_QUERIES and nx >= TOPK_TC_MIN_ITEMS))
     if use_tc:
         ws_bytes = lib().pb200_topk_tc_workspace_bytes(nq, nx, d, k)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
@@ -340,7 +342,7 @@ def hamming_topk(codes_q, codes_x, k, id_offset=0, precision="auto"):
         ok = bool(lib().pb200_hamming_topk_tc_supported(nq, nx, cb, k))
         if precision == "tc" and not ok:
             raise N.NativeError(f"hamming_topk: precision='tc' needs code_bytes <= 64, k <= 32 (got {cb}, {k})")
-        use_tc = ok and (precision == "tc" or nq >= TOPK_TC_MIN_QUERIES)
+        use_tc = ok and (precision == "tc" or (nq >= TOPK_TC_MIN_QUERIES and nx >= TOPK_TC_MIN_ITEMS))
     if use_tc:
         ws_bytes = lib().pb200_hamming_topk_tc_workspace_bytes(nq, nx, cb, k)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
