@@ -14,8 +14,10 @@ T=10 neighbours.  One step = 2 x [walk/count/top-T kernel over all items] + fuse
   cpu_baseline   the oracle port (C walk sampler on all host threads + numpy forward) on a
                  bounded sample, rank 0 at N=1
 
-N > 1 (torchrun): rows are split across ranks (strong scaling over the fixed catalogue), one
-all-gather of h per layer over NCCL; time = max over ranks.
+N > 1 (torchrun): rows are split across ranks (strong scaling over the fixed catalogue); the
+pooling kernel reads neighbour rows of h from peer memory over NVLink, one one-element
+all-reduce per layer as a barrier; the per-rank step is replayed as a CUDA graph (sampling
+epochs advance on the device); time = max over ranks.
 `--impl reference` times the CPU port alone (rank 0) and prints the same JSON shape.
 """
 import argparse
@@ -45,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=8192, help="start items per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["fp32", "tf32", "auto"])
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the sharded step eagerly")
     return ap.parse_args()
 
 
@@ -211,8 +214,12 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None   # N > 1: the sharded step is launch bound -> one CUDA graph per rank (graphs.py)
+
     def step_device(walk_events=None):
         if ws > 1:
+            if graphed is not None:
+                return graphed.replay()
             return SH.get_embeddings_sharded(model, x_dev, sampler, M, T)
         batches = []
         for layer in range(layers):
@@ -237,6 +244,12 @@ def main_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_device(); step_e2e()
     barrier()
+    if ws > 1 and not args.no_graph:
+        from mre_b200.graphs import GraphedEmbeddings
+        graphed = GraphedEmbeddings(model, x_dev, sampler, T, num_items=M)
+        for _ in range(3):
+            step_device()
+        barrier()
 
     # ---- timed: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
     walk_events, step_ms = [], []
@@ -254,6 +267,8 @@ def main_b200(args):
     barrier()
     wall_dev = time.perf_counter() - wall0
     launches = N.launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps   # replays bypass the ABI's launch counter
     dev_ms = sum(a.elapsed_time(b) for a, b in step_ms)
     walk_ms = [a.elapsed_time(b) for a, b in walk_events]
 
@@ -284,6 +299,8 @@ def main_b200(args):
             "config": dict(workload_config(args, inp, ws), l2="flushed between steps (256 MB "
                            "write); CSR 0.6 GB exceeds the 126 MB L2",
                            weights="seeded default init (torch.manual_seed(0))",
+                           step_launch="cuda graph replay per rank" if graphed is not None else "eager",
+                           exchange=os.environ.get("PB200_SHARD_EXCHANGE", "p2p") + " (neighbour rows of h)" if ws > 1 else "none",
                            csr_build_s=round(csr_s, 3), graph_gen_s=round(inp["gen_s"], 1),
                            csr_bytes=sampler.csr.nbytes(), walk_index_bytes=sampler.csr.index_nbytes(), wall_s_timed_region=round(wall_dev, 4)),
             "e2e": {"value": M * args.steps / e2e_s, "unit": UNIT,

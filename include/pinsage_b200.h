@@ -111,6 +111,19 @@ int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx, const uin
                             int32_t* out_ids, int32_t* out_counts, float* out_weights,
                             int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream);
 
+/* pb200_walk_topt_indexed with the sampling epoch advanced ON THE DEVICE: the effective epoch is
+ * epoch + *epoch_dev (epoch_dev: device uint32, may be NULL).  Lets a whole embedding step be
+ * captured in a CUDA graph whose replays still draw fresh walks: pb200_u32_add(epoch_dev, L)
+ * as the last node of the graph plays the role of the advancing global RNG stream
+ * (utils/random_walk.py:79; per-layer resampling at model/pinsage.py:271-275). */
+int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* idx, const uint32_t* leaf,
+                               int64_t num_nodes, const int32_t* starts, int64_t n, int num_walks,
+                               int walk_length, int num_neighbors, uint64_t seed, uint32_t epoch,
+                               const uint32_t* epoch_dev, int32_t* out_ids, int32_t* out_counts,
+                               float* out_weights, int32_t* out_nvalid, int32_t* trace_out,
+                               pb200_stream_t stream);
+int pb200_u32_add(uint32_t* counter, uint32_t delta, pb200_stream_t stream);
+
 /* Counting stage alone, given traces (parity "given the same walk traces"):
  * trace int32 [n, V] (V = W*L visits in walk-major order, -1 = none). */
 int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_start, int num_neighbors,
@@ -164,6 +177,15 @@ int pb200_peer_free(void* ptr);
 int pb200_peer_export(const void* ptr, uint8_t handle_out[PB200_PEER_HANDLE_BYTES]);
 int pb200_peer_open(const uint8_t handle[PB200_PEER_HANDLE_BYTES], void** ptr_out);
 int pb200_peer_close(void* ptr);
+
+/* Barrier between the ranks of one box on peer memory -- one tiny kernel, so it can sit inside a
+ * captured CUDA graph.  flag_ptrs_dev: DEVICE array of `world` pointers, entry r = rank r's flag
+ * array (uint32[world], zero-initialised peer buffer, valid in this process); seq_counter /
+ * error_flag: device uint32 owned by this rank (zero-initialised).  Everything this rank queued
+ * before the barrier is visible to its peers' kernels queued after theirs.  The wait is bounded;
+ * *error_flag becomes 1 if a peer never arrives. */
+int pb200_peer_barrier(uint32_t* const* flag_ptrs_dev, uint32_t* seq_counter, int rank, int world,
+                       uint32_t* error_flag, pb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * G1-G3  fused [gather -> importance sum -> concat -> dense -> epilogue]

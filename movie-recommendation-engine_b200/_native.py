@@ -37,6 +37,10 @@ SIGNATURES = {
     "pb200_walk_topt_indexed": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
                                         c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr]),
+    "pb200_walk_topt_indexed_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
+                                           c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                           c_ptr]),
+    "pb200_u32_add": (c_int, [c_ptr, c_u32, c_ptr]),
     "pb200_count_topt": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pb200_pool": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int,
                            c_ptr, c_ptr]),
@@ -47,6 +51,7 @@ SIGNATURES = {
     "pb200_peer_export": (c_int, [c_ptr, c_ptr]),
     "pb200_peer_open": (c_int, [c_ptr, c_ptr]),
     "pb200_peer_close": (c_int, [c_ptr]),
+    "pb200_peer_barrier": (c_int, [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
     "pb200_gather_dense": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
                                    c_int, c_int, c_ptr, c_ptr]),

@@ -147,6 +147,42 @@ extern "C" int pb200_pool_sharded(const float* const* shard_ptrs, int world, int
                        mode, out, (cudaStream_t)stream);
 }
 
+// ---- barrier between the ranks of one box on peer memory (a plain kernel: CUDA-graph capturable) ----
+// flags[r] points to rank r's flag array (uint32[world], peer memory).  Rank `rank` publishes its
+// next sequence number into slot [rank] of every rank's array and waits until all slots of its
+// own array have reached it.  The wait is bounded (~seconds): a dead peer must not hang the GPU;
+// on time-out *error_flag is set and the kernel returns.
+namespace pb200 {
+__global__ void peer_barrier_kernel(uint32_t* const* __restrict__ flags, uint32_t* seq_counter, int rank,
+                                    int world, uint32_t* error_flag) {
+    const int t = threadIdx.x;
+    const uint32_t seq = *seq_counter + 1u;
+    __threadfence_system();                       // this rank's earlier writes before its flag
+    if (t < world) {
+        volatile uint32_t* theirs = flags[t] + rank;
+        *theirs = seq;
+        volatile uint32_t* mine = flags[rank] + t;
+        unsigned long long spins = 0;
+        while ((int32_t)(*mine - seq) < 0) {
+            if (++spins > (1ull << 27)) { *error_flag = 1u; break; }
+            __nanosleep(40);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) *seq_counter = seq;
+}
+}  // namespace pb200
+
+extern "C" int pb200_peer_barrier(uint32_t* const* flag_ptrs_dev, uint32_t* seq_counter, int rank, int world,
+                                  uint32_t* error_flag, pb200_stream_t stream) {
+    PB_REQUIRE(flag_ptrs_dev && seq_counter && error_flag && world >= 1 && world <= PB200_MAX_PEERS &&
+               rank >= 0 && rank < world, "peer_barrier: bad arguments");
+    pb200::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_ptrs_dev, seq_counter, rank, world,
+                                                                     error_flag);
+    return check_launch("peer_barrier_kernel");
+}
+
 // ---- peer buffers: cudaMalloc'ed exchange buffers shared between the ranks of one box by CUDA IPC ----
 extern "C" int pb200_peer_alloc(size_t bytes, void** ptr_out) {
     PB_REQUIRE(ptr_out && bytes > 0, "peer_alloc: bad arguments");

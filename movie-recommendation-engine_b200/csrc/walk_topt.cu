@@ -37,6 +37,7 @@ struct WalkParams {
     int W, L, T;
     int slots, slot_shift;  // hash table size (power of two) and 32 - log2(slots)
     uint32_t seed_lo, seed_hi, epoch;
+    const uint32_t* __restrict__ epoch_dev;   // optional: added to epoch (CUDA-graph replays advance it on the device)
     int32_t* __restrict__ out_ids;
     int32_t* __restrict__ out_counts;
     float* __restrict__ out_w;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
             }
         } else {
             const int start = p.starts[s];
+            const uint32_t epoch = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
             for (int walk = lane; walk < p.W; walk += 32) {
                 int32_t* tr = p.trace_out ? p.trace_out + (s * p.W + walk) * p.L : nullptr;
                 int cur = start;
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
                 for (; l < p.L; ++l) {
                     if ((l & 1) == 0)
                         r = philox4x32_10((uint32_t)start, (uint32_t)walk, (uint32_t)(l >> 1),
-                                          p.epoch, p.seed_lo, p.seed_hi);
+                                          epoch, p.seed_lo, p.seed_hi);
                     const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
                                                  : uniform53(r.v[0], r.v[1]);
                     int next = -1;
@@ -456,13 +458,13 @@ extern "C" int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_
     return launch_walk(p, 0, true, (cudaStream_t)stream);
 }
 
-extern "C" int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx,
+extern "C" int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* idx,
                                        const uint32_t* leaf, int64_t num_nodes,
                                        const int32_t* starts, int64_t n, int num_walks,
                                        int walk_length, int num_neighbors, uint64_t seed,
-                                       uint32_t epoch, int32_t* out_ids, int32_t* out_counts,
-                                       float* out_weights, int32_t* out_nvalid, int32_t* trace_out,
-                                       pb200_stream_t stream) {
+                                       uint32_t epoch, const uint32_t* epoch_dev, int32_t* out_ids,
+                                       int32_t* out_counts, float* out_weights, int32_t* out_nvalid,
+                                       int32_t* trace_out, pb200_stream_t stream) {
     PB_REQUIRE(n >= 0 && num_walks > 0 && walk_length > 0 && num_neighbors > 0,
                "walk_topt_indexed: n=%lld W=%d L=%d T=%d must be positive", (long long)n,
                num_walks, walk_length, num_neighbors);
@@ -475,7 +477,30 @@ extern "C" int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx
     p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
     p.n = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.epoch = epoch;
+    p.epoch_dev = epoch_dev;
     p.out_ids = out_ids; p.out_counts = out_counts; p.out_w = out_weights;
     p.out_nvalid = out_nvalid; p.trace_out = trace_out;
     return launch_walk(p, 0, false, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx,
+                                       const uint32_t* leaf, int64_t num_nodes,
+                                       const int32_t* starts, int64_t n, int num_walks,
+                                       int walk_length, int num_neighbors, uint64_t seed,
+                                       uint32_t epoch, int32_t* out_ids, int32_t* out_counts,
+                                       float* out_weights, int32_t* out_nvalid, int32_t* trace_out,
+                                       pb200_stream_t stream) {
+    return pb200_walk_topt_indexed_ex(meta, idx, leaf, num_nodes, starts, n, num_walks, walk_length,
+                                      num_neighbors, seed, epoch, nullptr, out_ids, out_counts,
+                                      out_weights, out_nvalid, trace_out, stream);
+}
+
+namespace pb200 {
+__global__ void u32_add_kernel(uint32_t* p, uint32_t delta) { *p += delta; }
+}  // namespace pb200
+
+extern "C" int pb200_u32_add(uint32_t* counter, uint32_t delta, pb200_stream_t stream) {
+    PB_REQUIRE(counter, "u32_add: null pointer");
+    pb200::u32_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+    return check_launch("u32_add_kernel");
 }

@@ -127,8 +127,13 @@ def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_
     return build_walk_index(csr) if index else csr
 
 
+def u32_add(counter, delta):
+    """counter (device int32/uint32 scalar tensor) += delta, in stream order."""
+    check(lib().pb200_u32_add(ptr(counter), int(delta) & 0xFFFFFFFF, stream_ptr(counter.device)), "u32_add")
+
+
 def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epoch=0,
-              return_trace=False, use_index=True):
+              return_trace=False, use_index=True, epoch_dev=None):
     dev = csr.device
     s = N.dev_tensor(starts, torch.int32, dev)
     n = s.numel()
@@ -139,12 +144,15 @@ def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epo
     nvalid = torch.empty(n, dtype=torch.int32, device=dev)
     trace = torch.empty((n, num_walks, walk_length), dtype=torch.int32, device=dev) \
         if return_trace else None
+    if epoch_dev is not None and not (use_index and csr.meta is not None):
+        raise N.NativeError("walk_topt: a device-side epoch needs the sampling index (use_index=True)")
     if use_index and csr.meta is not None:
-        check(lib().pb200_walk_topt_indexed(ptr(csr.meta), ptr(csr.idx), ptr(csr.leaf),
-                                            csr.num_nodes, ptr(s), n, int(num_walks),
-                                            int(walk_length), T, int(seed) & (2**64 - 1),
-                                            int(epoch) & 0xFFFFFFFF, ptr(ids), ptr(counts),
-                                            ptr(weights), ptr(nvalid), ptr(trace), stream_ptr(dev)),
+        check(lib().pb200_walk_topt_indexed_ex(ptr(csr.meta), ptr(csr.idx), ptr(csr.leaf),
+                                               csr.num_nodes, ptr(s), n, int(num_walks),
+                                               int(walk_length), T, int(seed) & (2**64 - 1),
+                                               int(epoch) & 0xFFFFFFFF, ptr(epoch_dev), ptr(ids),
+                                               ptr(counts), ptr(weights), ptr(nvalid), ptr(trace),
+                                               stream_ptr(dev)),
               "walk_topt_indexed")
         return (ids, counts, weights, nvalid, trace) if return_trace else \
             (ids, counts, weights, nvalid)

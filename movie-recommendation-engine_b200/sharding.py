@@ -6,8 +6,10 @@ What shards and what is exchanged:
   * conv layers rows are split the same way; layer l+1 gathers rows of h^(l) from arbitrary
                 nodes.  On GPUs of one box the pooling kernel reads those rows straight from
                 their owner's memory over NVLink (CUDA IPC peer buffers, `PeerBuffers`; ~1.3
-                remote rows per node instead of the whole matrix) and the only collective is a
-                one-element all-reduce per layer as a stream-ordered barrier.  The all-gather
+                remote rows per node instead of the whole matrix) and the only synchronisation
+                is one flag barrier on peer memory per layer (pb200_peer_barrier: a kernel, so
+                the whole step can be replayed as a CUDA graph; NCCL collectives inside the
+                capture hung on this stack).  The all-gather
                 of the row shards of h is kept for CPU/gloo runs and the exact-fp32 path.
   * search      queries are split, the index is replicated, results are all-gathered; or items
                 are split (exact search on catalogues that do not fit one GPU), every rank
@@ -113,8 +115,30 @@ class PeerBuffers:
             raw = _RawCuda(self._own[b].value, (shard_rows, width))
             self._keep.append(raw)
             self._local.append(torch.as_tensor(raw, device=dev))
-        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.barrier()
+        # barrier state: one flag array per rank in peer memory + this rank's sequence counter
+        fp = ctypes.c_void_p()
+        N.check(lib.pb200_peer_alloc(256, ctypes.byref(fp)), "peer_alloc")
+        self._own.append(fp)
+        self._flags_local = torch.as_tensor(_RawCuda(fp.value, (64,)), device=dev)
+        self._flags_local.zero_()
+        fh = (ctypes.c_uint8 * 64)()
+        N.check(lib.pb200_peer_export(fp, fh), "peer_export")
+        fgath = [None] * self.ws
+        dist.all_gather_object(fgath, bytes(fh), group=group)
+        fptrs = []
+        for r in range(self.ws):
+            if r == self.rank:
+                fptrs.append(fp.value)
+            else:
+                q = ctypes.c_void_p()
+                N.check(lib.pb200_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(fgath[r]), ctypes.byref(q)),
+                        "peer_open")
+                self._opened.append(q)
+                fptrs.append(q.value)
+        self._flag_ptrs = torch.tensor(fptrs, dtype=torch.int64, device=dev)
+        self._seq = torch.zeros(2, dtype=torch.int32, device=dev)      # [sequence counter, error flag]
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                                     # every rank's flags are zeroed and mapped
 
     def ptr_array(self, b):
         return self._arrays[b]
@@ -123,9 +147,15 @@ class PeerBuffers:
         return self._local[b]
 
     def barrier(self):
-        """All ranks' work queued before this point is complete before anything queued after it
-        starts on any rank (a one-element all-reduce on the compute stream)."""
-        dist.all_reduce(self._flag, group=self.group)
+        """All ranks' work queued before this point is complete and visible before anything queued
+        after it starts on any rank: one small kernel on peer-memory flags (pb200_peer_barrier), so
+        a step containing it can be captured in a CUDA graph."""
+        from . import _native as N
+        N.check(N.lib().pb200_peer_barrier(N.ptr(self._flag_ptrs), N.ptr(self._seq[0:1]), self.rank, self.ws,
+                                           N.ptr(self._seq[1:2]), N.stream_ptr(self.dev)), "peer_barrier")
+
+    def timed_out(self):
+        return bool(self._seq[1].item())
 
     def close(self):
         from . import _native as N
@@ -135,7 +165,7 @@ class PeerBuffers:
             N.lib().pb200_peer_close(q)
         for p in self._own:
             N.lib().pb200_peer_free(p)
-        self._opened, self._own, self._local, self._keep = [], [], [], []
+        self._opened, self._own, self._local, self._keep, self._flags_local = [], [], [], [], None
 
 
 _PEER_CACHE = {}
@@ -164,9 +194,12 @@ def _use_peer_exchange(model, dev, ws):
     return dist.get_backend() == "nccl" and model.precision != N.PREC_FP32 and not model.fuse_pool
 
 
-def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None):
+def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None,
+                           epoch_base=None, epoch_dev=None):
     """PinSage.get_embeddings with rows split across ranks.  x_local: this rank's rows of the
-    feature matrix (shard_range layout).  Returns this rank's rows of the embeddings."""
+    feature matrix (shard_range layout).  Returns this rank's rows of the embeddings.
+    epoch_base / epoch_dev: fixed host epoch + device-side counter (CUDA-graph capture, see
+    graphs.GraphedEmbeddings); by default the sampler's own epoch counter advances."""
     from . import _native as N
     from . import kernels as K
     from . import neighbor_lists as NL
@@ -176,8 +209,9 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     xd = N.dev_tensor(x_local, torch.float32, dev)
     nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
     batches = []
-    for _ in range(model.num_layers):                       # same epochs on every rank
-        ids, _c, w, nv = sampler._sample(nodes, num_neighbors, check=False)
+    for layer in range(model.num_layers):                   # same epochs on every rank
+        ids, _c, w, nv = sampler._sample(nodes, num_neighbors, check=False, epoch_dev=epoch_dev,
+                                         epoch=None if epoch_base is None else epoch_base + layer)
         batches.append(NL.from_walk(ids, w, nv))
     P = lambda lin: (lin.weight, lin.bias)     # Parameter objects: identity keys the TF32 weight cache
     RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward

@@ -100,14 +100,14 @@ class RandomWalkSampler:
         ids, _counts, weights, nvalid = self._sample(nodes, num_neighbors)
         return NL.from_walk(ids, weights, nvalid)
 
-    def _sample(self, nodes, num_neighbors, epoch=None, check=True):
+    def _sample(self, nodes, num_neighbors, epoch=None, check=True, epoch_dev=None):
         if not isinstance(nodes, torch.Tensor):
             nodes = torch.as_tensor(list(nodes), dtype=torch.int64)
         nodes = nodes.reshape(-1)
         if check:
             self._check_nodes(nodes)
         return K.walk_topt(self.csr, nodes, self.num_walks, self.walk_length, num_neighbors,
-                           self.seed, self._next_epoch() if epoch is None else epoch)
+                           self.seed, self._next_epoch() if epoch is None else epoch, epoch_dev=epoch_dev)
 
     # ---- out of scope ------------------------------------------------------------------
     def compute_ppr_matrix(self, *a, **k):

@@ -206,3 +206,26 @@ def test_tcgen05_dense_many_tiles_per_cta(dev, fill):
             hh = h.clone(); K.lib().pb200_round_tf32(K.ptr(hh), K.ptr(hh), hh.numel(), None)
         got = K.gather_dense(hh, w, b, pool_x=hh, lists=lists, flags=flags, precision=N.PREC_TF32).cpu().numpy()
         assert Hh.rel_row_err(got, ref) < 1.5e-3
+
+
+def test_graphed_embeddings_replays_equal_eager_calls(dev):
+    """graphs.GraphedEmbeddings: replay k of the captured step == eager get_embeddings call k
+    (the sampling epoch advances on the device inside the graph)."""
+    from mre_b200 import synthetic as S
+    from mre_b200.graphs import GraphedEmbeddings
+    from mre_b200.model.pinsage import PinSage
+    from mre_b200.utils.random_walk import RandomWalkSampler
+    M, U, R = 1500, 4000, 60000
+    ei, w = S.bipartite_graph(M, U, R, seed=3)
+    x = S.features(M, 64).to(dev)
+    torch.manual_seed(0)
+    model = PinSage(64, 128, 64, 2).to(dev).eval()
+    sampler = RandomWalkSampler(torch.from_numpy(ei), torch.from_numpy(w), 2, 100, seed=7, device=dev, num_nodes=M + U)
+    sampler.epoch = 40
+    g = GraphedEmbeddings(model, x, sampler, 10)
+    outs = [g.replay().clone() for _ in range(3)]
+    assert not torch.equal(outs[0], outs[1])                 # fresh walks every replay
+    for k, got in enumerate(outs):
+        sampler.epoch = 40 + 2 * k
+        want = model.get_embeddings(x, sampler, 10)
+        assert torch.equal(got, want)

@@ -25,6 +25,16 @@ for prec in (N.PREC_FP32, N.PREC_AUTO):
     lo, hi = SH.shard_range(M, rank, ws)
     mine = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
     assert torch.equal(mine, full[lo:hi]), f"rank {rank}: sharded embeddings differ (precision {prec})"
+# CUDA-graph replays of the sharded step == eager sharded calls with the same epochs
+from mre_b200.graphs import GraphedEmbeddings
+model.precision = N.PREC_AUTO
+sampler.epoch = 100
+g = GraphedEmbeddings(model, x[lo:hi].to(dev), sampler, 10, num_items=M)
+for k in range(3):
+    got = g.replay().clone()
+    sampler.epoch = 100 + 2 * k
+    want = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
+    assert torch.equal(got, want), f"rank {rank}: graph replay {k} differs from the eager step"
 emb = full
 # item-sharded exact search + merge == unsharded
 q = emb[:257].contiguous()
