@@ -84,11 +84,14 @@ def main():
     lsh.build(x_np)
     cq = lsh.codes
     t_enc, _ = timed(lambda: K.lsh_encode(xd, lsh.projection))
-    t, (hd, hi) = timed(lambda: K.hamming_topk(cq, cq, k))
+    t, (hd, hi) = timed(lambda: K.hamming_topk(cq, cq, k, precision="tc"))
+    t_pop, (hd0, hi0) = timed(lambda: K.hamming_topk(cq, cq, k, precision="simt"), iters=1)
     t0 = time.perf_counter(); _d, ids = lsh.search(x_np, k); e2e = n / (time.perf_counter() - t0)
     lines.append(dict(base, method="lsh_exhaustive 256 bits (L1/L2, faiss.IndexLSH behaviour)", value=n / (t + t_enc),
                       ms=(t + t_enc) * 1e3, encode_ms=t_enc * 1e3, e2e=e2e, recall_at_10=recall(exact_ids, ids, k),
-                      popc64_per_s=n * n * 4 / t))
+                      hamming_ms=t * 1e3, kernel="tcgen05 +-1 bf16 GEMM + fused shortlist (exact)",
+                      equal_to_popcount_kernel=bool(torch.equal(hd, hd0) and torch.equal(hi, hi0)),
+                      popcount_kernel_ms=t_pop * 1e3, popcount_kernel_queries_per_s=n / (t_pop + t_enc)))
     # CPU restatement on a bounded sample of queries
     nq = min(args.cpu_queries, n)
     codes_np = cq.cpu().numpy()
@@ -112,13 +115,23 @@ def main():
     ivf = WeakANDIndex(d, 100, 10)
     t0 = time.perf_counter(); ivf.build(x_np); torch.cuda.synchronize(); build_s = time.perf_counter() - t0
 
-    def ivf_search():
+    def ivf_search_simt():
         _, probes = K.topk(xd, ivf.centroids, 20, N.METRIC_L2)
         return K.ivf_search(xd, probes, *ivf._lists, k)
-    t, (vd, vi) = timed(ivf_search)
+
+    ivf_stats = {}
+
+    def ivf_search_tc():
+        _, probes = K.topk(xd, ivf.centroids, 20, N.METRIC_L2)
+        return K.ivf_search_tc(xd, probes, *ivf._lists, ivf._tc_layout, 100, k, stats=ivf_stats)
+    t_simt, (vd0, vi0) = timed(ivf_search_simt, iters=1)
+    t, (vd, vi) = timed(ivf_search_tc)
     t0 = time.perf_counter(); _d, ids = ivf.search(x_np, k); e2e = n / (time.perf_counter() - t0)
-    lines.append(dict(base, method="ivf_weak_and nlist=100 nprobe=20 (I1/I2)", value=n / t, ms=t * 1e3, e2e=e2e,
-                      recall_at_10=recall(exact_ids, ids, k), build_s=build_s))
+    lines.append(dict(base, method="ivf_weak_and nlist=100 nprobe=20 (I1/I2) tcgen05 probe-masked shortlist + fp32 re-rank",
+                      value=n / t, ms=t * 1e3, e2e=e2e, recall_at_10=recall(exact_ids, ids, k), build_s=build_s,
+                      list_scan_reruns=int(ivf_stats["list_scan_reruns"].item()),
+                      bitwise_equal_to_list_scan_kernel=bool(torch.equal(vi, vi0) and torch.equal(vd, vd0)),
+                      list_scan_kernel_queries_per_s=n / t_simt, list_scan_kernel_ms=t_simt * 1e3))
     t0 = time.perf_counter()
     O.ivf_search(x_np, ivf.centroids.cpu().numpy(), ivf.assign.cpu().numpy(), x_np[:nq], k, 20)
     tc = time.perf_counter() - t0

@@ -321,6 +321,28 @@ int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* p
                      const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
                      pb200_stream_t stream);
 
+/* Same results as pb200_ivf_search (bit for bit) on the tensor cores.  The caller prepares, once
+ * per index, a padded list-ordered layout of the vectors (np rows, np % 128 == 0, every list
+ * starting at a multiple of 128):
+ *   xp        float32 [np, dim]  TF32-rounded vectors (zero rows as padding)
+ *   hxp       float32 [np + 128] 0.5 |x|^2 (+inf for padding rows)
+ *   src_pos   int32   [np]       row of list_vecs / list_ids for every padded row, -1 = padding
+ *   tile_list int32   [np / 128] list id of every 128-row tile
+ *   xstats    float32 [3] (device) max |x|^2, max |rna_tf32(x) - x|_2, max |rna_tf32(x)|_2
+ * The scoring GEMM covers all tiles; a query row scans a tile only if it probes the tile's
+ * list; exact fp32 re-rank with pb200_ivf_search's own distance arithmetic; queries whose result
+ * cannot be certified are re-run by the list-scan kernel from a device-side list.
+ * nlist <= 128, dim % 4 == 0, dim <= 256, k <= 24.  stats_out: optional DEVICE int32[1]. */
+int pb200_ivf_search_tc_supported(int64_t nq, int64_t np, int dim, int k, int nlist);
+size_t pb200_ivf_search_tc_workspace_bytes(int64_t nq, int64_t np, int dim, int k, int nlist, int nprobe);
+int pb200_ivf_search_tc(const float* queries, int64_t nq, int dim, const int32_t* probes, int nprobe,
+                        int nlist, const int32_t* list_offsets, const int32_t* list_ids,
+                        const float* list_vecs, const float* xp, const float* hxp,
+                        const int32_t* src_pos, const int32_t* tile_list, int64_t np,
+                        const uint32_t* xstats, int k, float* out_dist, int32_t* out_ids,
+                        void* workspace, size_t workspace_bytes, int32_t* stats_out,
+                        pb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,11 @@ SIGNATURES = {
     "pb200_hamming_topk_tc_workspace_bytes": (c_size, [c_i64, c_i64, c_int, c_int]),
     "pb200_hamming_topk_tc": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_i32, c_ptr, c_ptr, c_ptr,
                                       c_size, c_ptr]),
+    "pb200_ivf_search_tc_supported": (c_int, [c_i64, c_i64, c_int, c_int, c_int]),
+    "pb200_ivf_search_tc_workspace_bytes": (c_size, [c_i64, c_i64, c_int, c_int, c_int, c_int]),
+    "pb200_ivf_search_tc": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                    c_ptr, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_size, c_ptr,
+                                    c_ptr]),
     "pb200_lsh_tables_workspace_bytes": (c_size, [c_i64, c_int, c_int]),
     "pb200_lsh_build_tables": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_size,
                                        c_ptr]),

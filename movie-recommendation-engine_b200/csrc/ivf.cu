@@ -9,7 +9,7 @@
 // Centroid assignment and the quantizer top-nprobe reuse pb200_topk (topk.cu).
 #include <cub/device/device_radix_sort.cuh>
 
-#include "common.cuh"
+#include "ivf.cuh"
 
 namespace pb200 {
 
@@ -69,6 +69,11 @@ struct IvfSearchParams {
     const float* __restrict__ list_vecs;
     int k;
     float* __restrict__ out_dist; int32_t* __restrict__ out_ids;
+    // optional query selection (pb200_ivf_search_tc re-runs its uncertified queries here)
+    const int32_t* __restrict__ qsel; const int32_t* __restrict__ qsel_count; int64_t qsel_base;
+    // per-probe mode (few selected queries: one warp per (query, probe) instead of a 20-list
+    // chain per warp); partial lists [slot][nprobe][32] are merged by topk_merge_kernel
+    int per_probe; float* __restrict__ part_bad; int32_t* __restrict__ part_ids;
 };
 
 // One warp per query.  Each warp stages 32 list vectors at a time in shared memory with
@@ -79,11 +84,19 @@ __global__ void __launch_bounds__(128) ivf_search_kernel(const IvfSearchParams p
     const int d = p.d, ds = d + 1;
     float* qs = is + (size_t)warp * (d + 32 * ds);   // [d]
     float* ts = qs + d;                              // [32][ds]
-    const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (qi >= p.nq) return;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t slot = p.per_probe ? w / p.nprobe : w;
+    if (slot >= p.nq) return;
+    int64_t qi = slot;
+    if (p.qsel) {
+        if (p.qsel_base + slot >= *p.qsel_count) return;
+        qi = p.qsel[p.qsel_base + slot];
+    }
+    const int pi0 = p.per_probe ? (int)(w % p.nprobe) : 0;
+    const int pi1 = p.per_probe ? pi0 + 1 : p.nprobe;
     for (int c = lane; c < d; c += 32) qs[c] = p.q[qi * d + c];
     TopkLane e; e.bad = INFINITY; e.id = INT_MAX;
-    for (int pi = 0; pi < p.nprobe; ++pi) {
+    for (int pi = pi0; pi < pi1; ++pi) {
         const int l = p.probes[qi * p.nprobe + pi];
         if (l < 0) continue;  // warp-uniform
         const int a = p.list_offsets[l], b = p.list_offsets[l + 1];
@@ -103,6 +116,12 @@ __global__ void __launch_bounds__(128) ivf_search_kernel(const IvfSearchParams p
             const int id = lane < cnt ? p.list_ids[base + lane] : -1;
             topk_offer(e, dist, id, lane < cnt, p.k, lane);
         }
+    }
+    if (p.per_probe) {
+        const bool has = lane < p.k && e.id != INT_MAX;
+        p.part_ids[w * 32 + lane] = has ? e.id : -1;
+        p.part_bad[w * 32 + lane] = has ? e.bad : INFINITY;
+        return;
     }
     if (lane < p.k) {
         const bool has = e.id != INT_MAX;
@@ -179,17 +198,14 @@ extern "C" int pb200_ivf_centroid_update(const float* list_vecs, const int32_t* 
     return check_launch("ivf_centroid_kernel");
 }
 
-extern "C" int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* probes,
-                                int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
-                                const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
-                                pb200_stream_t stream) {
-    PB_REQUIRE(nq >= 0 && dim > 0 && nprobe > 0, "ivf_search: bad sizes");
-    PB_REQUIRE(k > 0 && k <= 32, "ivf_search: k must be in [1, 32]");
-    if (nq == 0) return PB200_OK;
-    PB_REQUIRE(queries && probes && list_offsets && list_ids && list_vecs && out_dist && out_ids,
-               "ivf_search: null pointer");
+namespace pb200 {
+int ivf_search_run(const float* queries, int64_t nq, int dim, const int32_t* probes, int nprobe,
+                   const int32_t* list_offsets, const int32_t* list_ids, const float* list_vecs, int k,
+                   float* out_dist, int32_t* out_ids, const int32_t* qsel, const int32_t* qsel_count,
+                   int64_t qsel_base, float* part_bad, int32_t* part_ids, cudaStream_t stream) {
+    const int per_probe = part_bad != nullptr;
     IvfSearchParams p{queries, nq, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k,
-                      out_dist, out_ids};
+                      out_dist, out_ids, qsel, qsel_count, qsel_base, per_probe, part_bad, part_ids};
     const int wpb = 4;
     const size_t smem = (size_t)wpb * (dim + 32 * (dim + 1)) * sizeof(float);
     if (smem > 200 * 1024) {
@@ -199,6 +215,21 @@ extern "C" int pb200_ivf_search(const float* queries, int64_t nq, int dim, const
     if (smem > 48 * 1024)
         PB_CUDA(cudaFuncSetAttribute(ivf_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    ivf_search_kernel<<<(unsigned)ceil_div(nq, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(p);
+    const int64_t warps = per_probe ? nq * nprobe : nq;
+    ivf_search_kernel<<<(unsigned)ceil_div(warps, wpb), wpb * 32, smem, stream>>>(p);
     return check_launch("ivf_search_kernel");
+}
+}  // namespace pb200
+
+extern "C" int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* probes,
+                                int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
+                                const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
+                                pb200_stream_t stream) {
+    PB_REQUIRE(nq >= 0 && dim > 0 && nprobe > 0, "ivf_search: bad sizes");
+    PB_REQUIRE(k > 0 && k <= 32, "ivf_search: k must be in [1, 32]");
+    if (nq == 0) return PB200_OK;
+    PB_REQUIRE(queries && probes && list_offsets && list_ids && list_vecs && out_dist && out_ids,
+               "ivf_search: null pointer");
+    return ivf_search_run(queries, nq, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k, out_dist,
+                          out_ids, nullptr, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }

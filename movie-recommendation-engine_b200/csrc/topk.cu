@@ -198,6 +198,18 @@ static int choose_splits(int64_t nq, int64_t nx) {
     return (int)(s < 1 ? 1 : s);
 }
 
+int topk_merge_run(const float* vals, const int32_t* ids, int64_t nq, int c, int vals_are_bad, int largest,
+                   int k, float* out_scores, int32_t* out_ids, const int32_t* qsel,
+                   const int32_t* qsel_count, int64_t qsel_base, cudaStream_t stream) {
+    MergeParams m{};
+    m.vals = vals; m.ids = ids; m.nq = nq; m.c = c; m.vals_are_bad = vals_are_bad; m.largest = largest;
+    m.k_pass = k; m.k_total = k; m.col_off = 0; m.use_floor = 0;
+    m.out_scores = out_scores; m.out_ids = out_ids;
+    m.qsel = qsel; m.qsel_count = qsel_count; m.qsel_base = qsel_base;
+    topk_merge_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(m);
+    return check_launch("topk_merge_kernel");
+}
+
 int row_sqnorm_run(const float* x, int64_t n, int d, float* out, cudaStream_t stream) {
     if (n <= 0) return PB200_OK;
     row_sqnorm_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, stream>>>(x, n, d, out);

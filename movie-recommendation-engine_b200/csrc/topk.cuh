@@ -19,4 +19,9 @@ int topk_fp32_run(const float* queries, int64_t nq, const float* items, int64_t 
                   int32_t* part_ids, int splits, const int32_t* qsel, const int32_t* qsel_count,
                   int64_t qsel_base, cudaStream_t stream);
 
+// One merge pass (k <= 32) of candidate lists vals/ids [nq, c] into out rows (slot -> qsel row).
+int topk_merge_run(const float* vals, const int32_t* ids, int64_t nq, int c, int vals_are_bad, int largest,
+                   int k, float* out_scores, int32_t* out_ids, const int32_t* qsel,
+                   const int32_t* qsel_count, int64_t qsel_base, cudaStream_t stream);
+
 }  // namespace pb200

@@ -28,6 +28,7 @@
 //      (topk.cu) through a device-side compacted list -- no host synchronisation.
 #include <cstdlib>
 
+#include "ivf.cuh"
 #include "tc_common.cuh"
 #include "topk.cuh"
 
@@ -50,6 +51,10 @@ struct SearchParams {
     int stages, align_slack;
     int kind;                        // 0: tf32 operands (32 per 128 B chunk row), 1: bf16 (64 per chunk row)
     const float* __restrict__ hx;    // 0.5 |x|^2, padded to a multiple of 128 items (L2 only)
+    // IVF (pb200_ivf_search_tc): items are list ordered, every list padded to whole 128-item tiles;
+    // a row scans a tile only if its query probes the tile's list
+    const int32_t* __restrict__ tile_list;   // [nx / 128] list id of every item tile (NULL: no masking)
+    const uint32_t* __restrict__ pmask;      // [nq][4] bit l = query probes list l (nlist <= 128)
     unsigned long long* short_keys;  // [splits][nq][ks]   sorted, 0 = empty; slot = first chunk of a segment
 };
 
@@ -265,8 +270,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
             for (int i = lane; i < 32 * ks; i += 32) wl[i] = 0ull;
             __syncwarp();
             float thr = row_ok ? -INFINITY : INFINITY;      // score of rank ks-1 once the list is full
+            uint4 pm = make_uint4(0u, 0u, 0u, 0u);
+            if (p.pmask && row_ok) pm = __ldg(reinterpret_cast<const uint4*>(p.pmask) + q);
             for (int nt = 0; nt < ntiles; ++nt, ++tc_) {
                 const int b = tc_ & 1, ub = tc_ >> 1;
+                bool elig = true;                           // IVF: does this row's query probe the tile's list?
+                if (p.tile_list) {
+                    const int l = __ldg(p.tile_list + (n_begin / kTileN + nt));
+                    const uint32_t w = l < 32 ? pm.x : (l < 64 ? pm.y : (l < 96 ? pm.z : pm.w));
+                    elig = l >= 0 && ((w >> (l & 31)) & 1u);
+                }
+                float thr_t = elig ? thr : INFINITY;
                 mbar_wait(bar(kBarTFull + b), (uint32_t)(ub & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
@@ -295,12 +309,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
                         }
                         const float gm = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])),
                                                fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
-                        if (__any_sync(kFull, gm >= thr)) {
+                        if (__any_sync(kFull, gm >= thr_t)) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int col = col0 + g * 8 + i;
-                                const unsigned m = __ballot_sync(kFull, f[i] >= thr && col < n_end);
-                                if (m) thr = insert_column(m, f[i], 0xFFFFFFFFu - (uint32_t)col, wl, ks, lane, thr);
+                                const unsigned m = __ballot_sync(kFull, f[i] >= thr_t && col < n_end);
+                                if (m) {
+                                    thr = insert_column(m, f[i], 0xFFFFFFFFu - (uint32_t)col, wl, ks, lane, thr);
+                                    thr_t = elig ? thr : INFINITY;
+                                }
                             }
                         }
                     }
@@ -386,6 +403,10 @@ struct RerankParams {
     const unsigned long long* __restrict__ short_keys;
     float* __restrict__ out_scores; int32_t* __restrict__ out_ids;
     int32_t* qsel; int32_t* qsel_count;
+    // IVF mode: shortlisted positions are rows of the padded list-ordered copy; src_pos maps them
+    // to list order (-1 = padding), x = list_vecs (fp32, list order), ids_map = list_ids, and the
+    // distance is the direct form sum (q - v)^2 of ivf_search_kernel (same arithmetic, same order)
+    const int32_t* __restrict__ src_pos; const int32_t* __restrict__ ids_map;
 };
 
 __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
@@ -415,7 +436,25 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         const uint32_t col = 0xFFFFFFFFu - (uint32_t)key;
         float bad = INFINITY;
         int gid = -1;
-        if (valid) {
+        if (valid && p.src_pos) {
+            const int pos = p.src_pos[col];
+            valid = pos >= 0;
+            if (valid) {
+                const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)pos * p.d);
+                float dist = 0.f;
+                for (int c4 = 0; c4 < p.d / 4; ++c4) {
+                    const float4 xv = __ldg(xr + c4);
+                    const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * c4);
+                    float t = qv.x - xv.x; dist = fmaf(t, t, dist);
+                    t = qv.y - xv.y; dist = fmaf(t, t, dist);
+                    t = qv.z - xv.z; dist = fmaf(t, t, dist);
+                    t = qv.w - xv.w; dist = fmaf(t, t, dist);
+                }
+                bad = dist;
+                gid = p.ids_map[pos];
+                valid = bad == bad;
+            }
+        } else if (valid) {
             // the fp32 kernel's arithmetic: acc = fmaf(q[c], x[c], acc), c ascending
             const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)col * p.d);
             float acc = 0.f;
@@ -443,9 +482,9 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
                                    p.q_resid[q] * __uint_as_float(p.xmax_bits[2]) +
                                    (float)p.d * 2.384185791015625e-07f * qnorm * xnorm);
         // an outside item's `bad` is at least this:
-        const float bound = p.metric == PB200_METRIC_IP
-                                ? -(tt + eps)
-                                : qn - 2.f * (tt + eps) - 4e-6f * (qn + xmax);
+        // (IVF: the direct-form distance and |q|^2 carry ~d 2^-24 relative rounding each)
+        const float slack = p.src_pos ? (float)p.d * 2.4e-7f * (qn + xmax) : 4e-6f * (qn + xmax);
+        const float bound = p.metric == PB200_METRIC_IP ? -(tt + eps) : qn - 2.f * (tt + eps) - slack;
         certified = bad_k < bound;
     }
     if (certified) {
@@ -824,4 +863,166 @@ extern "C" int pb200_hamming_topk_tc(const uint8_t* codes_q, int64_t nq, const u
     tcs::hamming_finish_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(
         sp.short_keys, nq, pl.splits, pl.ks, k, nbits, id_offset, out_dist, out_ids);
     return check_launch("hamming_finish_kernel");
+}
+
+
+// =====================================================================================
+// IVF "Weak AND" search (WeakANDIndex.search, utils/nearest_neighbors.py:115-139) on the
+// tensor cores: the items are the list-ordered vectors with every list padded to whole
+// 128-item tiles (TF32-rounded copy `xp`), the scoring GEMM covers all of them, and a row
+// scans a tile only if its query probes the tile's list (128-bit probe mask per query) -- the
+// lists a query does not probe never reach its shortlist.  Exact fp32 re-rank with
+// ivf_search_kernel's direct-form distance, certificate as in pb200_topk_tc, uncertified
+// queries re-run by ivf_search_kernel: results equal pb200_ivf_search bit for bit.
+// =====================================================================================
+namespace pb200 {
+namespace tcs {
+
+__global__ void probe_mask_kernel(const int32_t* __restrict__ probes, int64_t nq, int nprobe, uint4* __restrict__ pmask) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int j = 0; j < nprobe; ++j) {
+            const int l = probes[q * nprobe + j];
+            if (l >= 0 && l < 128) w[l >> 5] |= 1u << (l & 31);
+        }
+        pmask[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+struct IPlan { Plan g; int64_t cap_pp; size_t off_qr, off_qn, off_qres, off_misc, off_pmask, off_short, off_qsel, off_pbad, off_pids, total; };
+
+static bool make_iplan(int64_t nq, int64_t np, int dim, int k, int nlist, int nprobe, IPlan* ip) {
+    if (dim % 4 || dim > 256 || dim <= 0 || nq <= 0 || np <= 0 || np % kTileN || nlist > 128 || k <= 0 || k > 24)
+        return false;
+    IPlan h{};
+    h.g.ks = k <= 12 ? 16 : 32;
+    h.g.nchunks = (dim + kChunkK - 1) / kChunkK;
+    if (!make_geometry(nq, np, h.g)) return false;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t r = off; off += align_up(bytes, 256); return r; };
+    h.off_qr = take((size_t)nq * dim * 4);
+    h.off_qn = take((size_t)nq * 4);
+    h.off_qres = take((size_t)nq * 4);
+    h.off_misc = take(256);
+    h.off_pmask = take((size_t)nq * 16);
+    h.off_short = take((size_t)h.g.splits * nq * h.g.ks * 8);
+    h.off_qsel = take((size_t)nq * 4);
+    h.cap_pp = nq < 4096 ? nq : 4096;     // uncertified queries re-run with one warp per (query, probe)
+    h.off_pbad = take((size_t)h.cap_pp * nprobe * 32 * 4);
+    h.off_pids = take((size_t)h.cap_pp * nprobe * 32 * 4);
+    h.total = off;
+    *ip = h;
+    return true;
+}
+
+}  // namespace tcs
+}  // namespace pb200
+
+extern "C" int pb200_ivf_search_tc_supported(int64_t nq, int64_t np, int dim, int k, int nlist) {
+    tcs::IPlan h;
+    return tcs::make_iplan(nq, np, dim, k, nlist, 1, &h) ? 1 : 0;
+}
+
+extern "C" size_t pb200_ivf_search_tc_workspace_bytes(int64_t nq, int64_t np, int dim, int k, int nlist,
+                                                      int nprobe) {
+    tcs::IPlan h;
+    return tcs::make_iplan(nq, np, dim, k, nlist, nprobe, &h) ? h.total : 0;
+}
+
+extern "C" int pb200_ivf_search_tc(const float* queries, int64_t nq, int dim, const int32_t* probes, int nprobe,
+                                   int nlist, const int32_t* list_offsets, const int32_t* list_ids,
+                                   const float* list_vecs, const float* xp, const float* hxp,
+                                   const int32_t* src_pos, const int32_t* tile_list, int64_t np,
+                                   const uint32_t* xstats, int k, float* out_dist, int32_t* out_ids,
+                                   void* workspace, size_t workspace_bytes, int32_t* stats_out,
+                                   pb200_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PB_REQUIRE(nq >= 0 && dim > 0 && nprobe > 0 && k > 0, "ivf_search_tc: bad sizes");
+    if (nq == 0) return PB200_OK;
+    tcs::IPlan h;
+    if (!tcs::make_iplan(nq, np, dim, k, nlist, nprobe, &h)) {
+        set_error("ivf_search_tc: needs dim %% 4 == 0, dim <= 256, k <= 24, nlist <= 128, padded items %% 128 == 0 "
+                  "(got dim=%d k=%d nlist=%d np=%lld)", dim, k, nlist, (long long)np);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    PB_REQUIRE(queries && probes && list_offsets && list_ids && list_vecs && xp && hxp && src_pos && tile_list &&
+               xstats && out_dist && out_ids && workspace, "ivf_search_tc: null pointer");
+    PB_REQUIRE(((uintptr_t)queries | (uintptr_t)xp | (uintptr_t)list_vecs | (uintptr_t)workspace) % 16 == 0,
+               "ivf_search_tc: queries / xp / list_vecs / workspace must be 16-byte aligned");
+    if (workspace_bytes < h.total) {
+        set_error("ivf_search_tc: workspace %zu B < required %zu B", workspace_bytes, h.total);
+        return PB200_ERR_WORKSPACE;
+    }
+    const tcs::Plan& pl = h.g;
+    char* ws = static_cast<char*>(workspace);
+    float* qr = reinterpret_cast<float*>(ws + h.off_qr);
+    float* qn = reinterpret_cast<float*>(ws + h.off_qn);
+    float* q_resid = reinterpret_cast<float*>(ws + h.off_qres);
+    int32_t* qsel_count = reinterpret_cast<int32_t*>(ws + h.off_misc + 64);
+    uint4* pmask = reinterpret_cast<uint4*>(ws + h.off_pmask);
+    int32_t* qsel = reinterpret_cast<int32_t*>(ws + h.off_qsel);
+    PB_CUDA(cudaMemsetAsync(ws + h.off_misc, 0, 256, stream));
+    tcs::round_rows_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(queries, qr, nq, dim, q_resid, nullptr);
+    int rc = check_launch("round_rows_kernel");
+    if (rc) return rc;
+    rc = row_sqnorm_run(queries, nq, dim, qn, stream);
+    if (rc) return rc;
+    {
+        const int64_t blocks = ceil_div(nq, 256) < kSMs * 8 ? ceil_div(nq, 256) : kSMs * 8;
+        tcs::probe_mask_kernel<<<(unsigned)blocks, 256, 0, stream>>>(probes, nq, nprobe, pmask);
+        rc = check_launch("probe_mask_kernel");
+        if (rc) return rc;
+    }
+    alignas(64) CUtensorMap tm_q, tm_x;
+    if (!make_map(&tm_q, qr, nq, dim, tc::kTileM) || !make_map(&tm_x, xp, np, dim, tcs::kTileN)) {
+        set_error("ivf_search_tc: cuTensorMapEncodeTiled failed (nq=%lld np=%lld dim=%d)", (long long)nq,
+                  (long long)np, dim);
+        return PB200_ERR_CUDA;
+    }
+    tcs::SearchParams sp{};
+    sp.nq = nq; sp.nx = np; sp.d = dim; sp.nchunks = pl.nchunks; sp.qt = pl.qt; sp.ks = pl.ks;
+    sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack;
+    sp.kind = 0; sp.hx = hxp; sp.tile_list = tile_list; sp.pmask = reinterpret_cast<const uint32_t*>(pmask);
+    sp.short_keys = reinterpret_cast<unsigned long long*>(ws + h.off_short);
+    PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
+    if (pl.ctas_per_sm == 2) {
+        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_L2, 2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        tcs::search_tc_kernel<PB200_METRIC_L2, 2><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
+    } else {
+        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_L2, 1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        tcs::search_tc_kernel<PB200_METRIC_L2, 1><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
+    }
+    rc = check_launch("search_tc_kernel");
+    if (rc) return rc;
+
+    tcs::RerankParams rp{};
+    rp.q = queries; rp.x = list_vecs; rp.nq = nq; rp.nx = np; rp.d = dim; rp.k = k; rp.ks = pl.ks;
+    rp.splits = pl.splits; rp.metric = PB200_METRIC_L2; rp.qn = qn; rp.xn = nullptr; rp.xmax_bits = xstats;
+    rp.q_resid = q_resid; rp.exclude = nullptr; rp.id_offset = 0; rp.short_keys = sp.short_keys;
+    rp.out_scores = out_dist; rp.out_ids = out_ids; rp.qsel = qsel; rp.qsel_count = qsel_count;
+    rp.src_pos = src_pos; rp.ids_map = list_ids;
+    tcs::rerank_kernel<<<(unsigned)ceil_div(nq, 8), 256, (size_t)8 * dim * 4, stream>>>(rp);
+    rc = check_launch("rerank_kernel");
+    if (rc) return rc;
+    // uncertified queries: the list-scan kernel on the compacted list (device-side count); the first
+    // cap_pp of them with one warp per (query, probe) + merge -- a handful of queries would otherwise
+    // wait for one warp to walk all nprobe lists (6 ms at C4) -- the rest one warp per query
+    float* part_bad = reinterpret_cast<float*>(ws + h.off_pbad);
+    int32_t* part_ids = reinterpret_cast<int32_t*>(ws + h.off_pids);
+    rc = ivf_search_run(queries, h.cap_pp, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k, out_dist,
+                        out_ids, qsel, qsel_count, 0, part_bad, part_ids, stream);
+    if (rc) return rc;
+    rc = topk_merge_run(part_bad, part_ids, h.cap_pp, nprobe * 32, 1, 0, k, out_dist, out_ids, qsel, qsel_count, 0,
+                        stream);
+    if (rc) return rc;
+    if (nq > h.cap_pp) {
+        rc = ivf_search_run(queries, nq - h.cap_pp, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k,
+                            out_dist, out_ids, qsel, qsel_count, h.cap_pp, nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
+    if (stats_out)
+        PB_CUDA(cudaMemcpyAsync(stats_out, qsel_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    return PB200_OK;
 }

@@ -414,6 +414,66 @@ def ivf_centroid_update(list_vecs, offsets, centroids):
     return centroids
 
 
+def ivf_tc_layout(offsets, list_ids, list_vecs, nlist):
+    """Padded list-ordered layout for pb200_ivf_search_tc (built once per index): every list starts
+    at a multiple of 128 rows.  Returns (xp, hxp, src_pos, tile_list, xstats) or None when the
+    shape is not covered (nlist > 128, dim % 4 != 0, dim > 256, empty index)."""
+    dev = list_vecs.device
+    n, d = list_vecs.shape
+    if n == 0 or nlist > 128 or d % 4 or d > 256:
+        return None
+    offs = offsets.to(torch.int64)
+    lens = offs[1:] - offs[:-1]
+    padded = (lens + 127) // 128 * 128
+    pstart = torch.cumsum(padded, 0) - padded
+    np_rows = int(padded.sum().item())
+    if np_rows == 0:
+        return None
+    # list l occupies padded rows [pstart[l], pstart[l] + lens[l]): row p of list order goes to
+    # pstart[list(p)] + (p - offs[list(p)])
+    lid = torch.repeat_interleave(torch.arange(nlist, device=dev), lens)
+    pos = torch.arange(n, device=dev, dtype=torch.int64)
+    dst = pstart[lid] + (pos - offs[:-1][lid])
+    src_pos = torch.full((np_rows,), -1, dtype=torch.int32, device=dev)
+    src_pos[dst] = pos.to(torch.int32)
+    tile_list = torch.repeat_interleave(torch.arange(nlist, device=dev, dtype=torch.int32), padded // 128).contiguous()
+    vec = torch.zeros((np_rows, d), dtype=torch.float32, device=dev)
+    vec[dst] = list_vecs
+    xp = torch.empty_like(vec)
+    check(lib().pb200_round_tf32(ptr(vec), ptr(xp), vec.numel(), stream_ptr(dev)), "round_tf32")
+    xn = (vec.double() * vec.double()).sum(1)
+    hxp = torch.full((np_rows + 128,), float("inf"), dtype=torch.float32, device=dev)
+    hxp[dst] = (0.5 * xn[dst]).float()
+    resid = (xp.double() - vec.double()).norm(dim=1).max() * 1.0001
+    xstats = torch.stack([xn.max() * 1.0001, resid, xp.double().norm(dim=1).max() * 1.0001]).float().contiguous()
+    return xp, hxp.contiguous(), src_pos.contiguous(), tile_list, xstats
+
+
+def ivf_search_tc(queries, probes, offsets, list_ids, list_vecs, layout, nlist, k, stats=None):
+    """pb200_ivf_search_tc: tensor-core scoring of the padded list-ordered vectors, probe-masked
+    shortlists, exact re-rank; equal to ivf_search bit for bit."""
+    dev = N.device_of(list_vecs)
+    xp, hxp, src_pos, tile_list, xstats = layout
+    nq, d = queries.shape
+    np_rows = xp.size(0)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    ws_bytes = lib().pb200_ivf_search_tc_workspace_bytes(nq, np_rows, d, k, nlist, probes.size(1))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    reruns = torch.zeros(1, dtype=torch.int32, device=dev) if stats is not None else None
+    check(lib().pb200_ivf_search_tc(ptr(queries), nq, d, ptr(probes), probes.size(1), nlist, ptr(offsets),
+                                    ptr(list_ids), ptr(list_vecs), ptr(xp), ptr(hxp), ptr(src_pos),
+                                    ptr(tile_list), np_rows, ptr(xstats), k, ptr(dist), ptr(ids), ptr(ws),
+                                    ws_bytes, ptr(reruns), stream_ptr(dev)), "ivf_search_tc")
+    if stats is not None:
+        stats.update(path="tf32", list_scan_reruns=reruns)
+    return dist, ids
+
+
+def ivf_search_tc_supported(nq, np_rows, d, k, nlist):
+    return bool(lib().pb200_ivf_search_tc_supported(nq, np_rows, d, k, nlist))
+
+
 def ivf_search(queries, probes, offsets, list_ids, list_vecs, k):
     dev = N.device_of(list_vecs)
     nq, d = queries.shape

@@ -131,6 +131,8 @@ class WeakANDIndex:
                                            is_trained=centroids is not None)
         self._x = torch.empty((0, dim), dtype=torch.float32, device=self.device)
         self._lists = None
+        self._tc_layout = None
+        self.precision = "auto"      # "fp32": always the list-scan kernel; "auto": tensor cores for >= 256 queries
 
     def build(self, embeddings):
         """reference :94-113: train (k-means) + add."""
@@ -145,6 +147,8 @@ class WeakANDIndex:
         _, a = K.topk(self._x, self.centroids, 1, N.METRIC_L2)
         self.assign = a.view(-1).contiguous()
         self._lists = K.ivf_build(self._x, self.assign, self.num_partitions)
+        # padded list-ordered TF32 copy for the tensor-core search path (None: shape not covered)
+        self._tc_layout = K.ivf_tc_layout(*self._lists, self.num_partitions)
         self.index.ntotal = self._x.size(0)
         print(f"Built Weak AND index with {x.size(0)} embeddings")
 
@@ -157,7 +161,12 @@ class WeakANDIndex:
             q = q[None]
         self.index.nprobe = min(self.num_partitions, 20)                       # :134
         _, probes = K.topk(q, self.centroids, self.index.nprobe, N.METRIC_L2)
-        dist, ids = K.ivf_search(q, probes, *self._lists, k)
+        lay = getattr(self, "_tc_layout", None)
+        if (self.precision != "fp32" and lay is not None and q.size(0) >= K.TOPK_TC_MIN_QUERIES
+                and K.ivf_search_tc_supported(q.size(0), lay[0].size(0), self.dim, k, self.num_partitions)):
+            dist, ids = K.ivf_search_tc(q, probes, *self._lists, lay, self.num_partitions, k)
+        else:
+            dist, ids = K.ivf_search(q, probes, *self._lists, k)
         return _np_results(dist, ids)
 
 

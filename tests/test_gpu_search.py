@@ -259,3 +259,26 @@ def test_hamming_topk_tensor_core_equals_popcount_kernel(K, nq, nx, code_bytes, 
     d1, i1 = K.hamming_topk(cx, cx, min(k, 16), precision="tc")
     d0, i0 = K.hamming_topk(cx, cx, min(k, 16), precision="simt")
     assert torch.equal(d1, d0) and torch.equal(i1, i0)
+
+
+# ---- tensor-core IVF search (pb200_ivf_search_tc): equal to the list-scan kernel -----------------
+@pytest.mark.parametrize("n,d,nlist,nq,k", [(6000, 64, 37, 700, 10), (20000, 128, 100, 1000, 10),
+                                            (3000, 32, 128, 300, 5), (9000, 128, 100, 513, 20)])
+def test_ivf_search_tensor_core_equals_list_scan(K, n, d, nlist, nq, k):
+    from mre_b200 import _native as N
+    rng = np.random.Generator(np.random.PCG64(n + nq))
+    cen = rng.standard_normal((nlist, d)).astype(np.float32)
+    x = (cen[rng.integers(0, nlist, n)] + 0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    q = (x[rng.integers(0, n, nq)] + 0.05 * rng.standard_normal((nq, d))).astype(np.float32)
+    xd, qd, cd = torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda(), torch.from_numpy(cen).cuda()
+    _, a = K.topk(xd, cd, 1, N.METRIC_L2)
+    lists = K.ivf_build(xd, a.view(-1).contiguous(), nlist)
+    lay = K.ivf_tc_layout(*lists, nlist)
+    assert lay is not None
+    _, probes = K.topk(qd, cd, min(nlist, 20), N.METRIC_L2)
+    st = {}
+    d1, i1 = K.ivf_search_tc(qd, probes, *lists, lay, nlist, k, stats=st)
+    d0, i0 = K.ivf_search(qd, probes, *lists, k)
+    np.testing.assert_array_equal(i1.cpu().numpy(), i0.cpu().numpy())
+    np.testing.assert_array_equal(d1.cpu().numpy(), d0.cpu().numpy())
+    assert int(st["list_scan_reruns"].item()) < nq // 2
