@@ -13,6 +13,7 @@ queries/s through the drop-in class with host numpy in/out, recall@10 vs exact
 queries ("restatement, not faiss": faiss is absent offline).
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -42,6 +43,13 @@ def recall(exact_ids, ids, k):
 
 
 def main():
+    with contextlib.redirect_stdout(sys.stderr):
+        lines = _run()
+    for l in lines:
+        print(json.dumps(l))
+
+
+def _run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=62423)
     ap.add_argument("--d", type=int, default=128)
@@ -139,7 +147,7 @@ def main():
                                      cores=torch.get_num_threads(), sample=f"{nq} queries")
     for l in lines:
         l["metric"] = "top-10 queries/sec"
-        print(json.dumps(l))
+    return lines
 
 
 if __name__ == "__main__":
