@@ -270,6 +270,14 @@ int pb200_topk_merge(const float* scores, const int32_t* ids, int64_t nq, int c,
 int pb200_lsh_encode(const float* x, int64_t n, int dim, const float* proj, int nbits,
                      uint8_t* codes, float* proj_out, pb200_stream_t stream);
 
+/* Same codes as pb200_lsh_encode, bit for bit, with the projection on the tensor cores (tcgen05
+ * TF32 kernel of pb200_gather_dense + a sign-packing kernel); projections smaller than the
+ * measured TF32 error bound are recomputed in fp32 with pb200_lsh_encode's arithmetic.
+ * dim % 4 == 0, 16-byte aligned x / proj / workspace. */
+size_t pb200_lsh_encode_tc_workspace_bytes(int64_t n, int dim, int nbits);
+int pb200_lsh_encode_tc(const float* x, int64_t n, int dim, const float* proj, int nbits,
+                        uint8_t* codes, void* workspace, size_t workspace_bytes, pb200_stream_t stream);
+
 /* exhaustive Hamming top-k over all stored codes (what the reference computes).
  * out_dist float32 [nq,k] (Hamming counts as floats, like faiss), out_ids int32 [nq,k]. */
 int pb200_hamming_topk(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x, int64_t nx,

@@ -28,6 +28,7 @@
 //      (topk.cu) through a device-side compacted list -- no host synchronisation.
 #include <cstdlib>
 
+#include "dense.cuh"
 #include "ivf.cuh"
 #include "tc_common.cuh"
 #include "topk.cuh"
@@ -1024,5 +1025,111 @@ extern "C" int pb200_ivf_search_tc(const float* queries, int64_t nq, int dim, co
     }
     if (stats_out)
         PB_CUDA(cudaMemcpyAsync(stats_out, qsel_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    return PB200_OK;
+}
+
+
+// =====================================================================================
+// LSH hash (LSHIndex.build / the query side of .search, utils/nearest_neighbors.py:35-43,
+// 59-66; faiss IndexLSH: y = A x, bit j = y_j >= 0) on the tensor cores: Y = X A^T by the
+// tcgen05 TF32 kernel of pb200_gather_dense, then one warp per vector packs the sign bits.
+// Every |y| below the measured TF32 error bound is recomputed in fp32 with
+// lsh_encode_kernel's own arithmetic (sequential fmaf over d), so the codes are bit-identical
+// to pb200_lsh_encode (about 1 % of the projections at C3).
+// =====================================================================================
+namespace pb200 {
+namespace tcs {
+
+__global__ void __launch_bounds__(256) lsh_pack_kernel(const float* __restrict__ x, int64_t n, int d,
+                                                       const float* __restrict__ proj, int nbits, int bit0,
+                                                       int nb, const float* __restrict__ y,
+                                                       const unsigned int* __restrict__ astats,
+                                                       uint8_t* __restrict__ codes) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* xr = x + row * d;
+    float n2 = 0.f, r2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float v = __ldg(xr + c);
+        const float e = __uint_as_float(to_tf32(v)) - v;
+        n2 = fmaf(v, v, n2); r2 = fmaf(e, e, r2);
+    }
+    for (int o = 16; o > 0; o >>= 1) { n2 += __shfl_xor_sync(kFull, n2, o); r2 += __shfl_xor_sync(kFull, r2, o); }
+    const float xnorm = sqrtf(n2) * 1.0001f, xres = sqrtf(r2) * 1.0001f;
+    // |<x~,a~> - <x,a>| <= |x| max|a~ - a| + |x~ - x| max|a~|  + accumulation slack
+    const float amax = __uint_as_float(astats[1]);
+    const float eps = 1.02f * (xnorm * __uint_as_float(astats[0]) + xres * amax +
+                               (float)d * 2.384185791015625e-07f * xnorm * amax);
+    // lane owns byte `lane` of this 256-bit chunk: bits 8 lane .. 8 lane + 7
+    if (lane * 8 >= nb) return;
+    const float4 y0 = *reinterpret_cast<const float4*>(y + row * nb + lane * 8);
+    const float4 y1 = *reinterpret_cast<const float4*>(y + row * nb + lane * 8 + 4);
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    uint32_t byte = 0u;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        float v = yy[b];
+        if (!(fabsf(v) >= eps)) {                      // uncertain (or NaN): exact fp32, reference order
+            const float* a = proj + (int64_t)(bit0 + lane * 8 + b) * d;
+            v = 0.f;
+            for (int k = 0; k < d; ++k) v = fmaf(__ldg(a + k), __ldg(xr + k), v);
+        }
+        byte |= (v >= 0.f ? 1u : 0u) << b;
+    }
+    codes[row * (nbits / 8) + bit0 / 8 + lane] = (uint8_t)byte;
+}
+
+}  // namespace tcs
+}  // namespace pb200
+
+extern "C" size_t pb200_lsh_encode_tc_workspace_bytes(int64_t n, int dim, int nbits) {
+    const int nb = nbits < 256 ? nbits : 256;
+    return align_up((size_t)(nbits > 0 ? nbits : 1) * dim * 4, 256) + align_up((size_t)(n > 0 ? n : 1) * nb * 4, 256) + 256;
+}
+
+extern "C" int pb200_lsh_encode_tc(const float* x, int64_t n, int dim, const float* proj, int nbits,
+                                   uint8_t* codes, void* workspace, size_t workspace_bytes,
+                                   pb200_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PB_REQUIRE(n >= 0 && dim > 0 && nbits > 0 && nbits % 32 == 0,
+               "lsh_encode_tc: nbits must be a positive multiple of 32");
+    if (n == 0) return PB200_OK;
+    PB_REQUIRE(x && proj && codes && workspace, "lsh_encode_tc: null pointer");
+    if (dim % 4 || ((uintptr_t)x | (uintptr_t)proj | (uintptr_t)workspace) % 16) {
+        set_error("lsh_encode_tc: needs dim %% 4 == 0 and 16-byte aligned x / proj / workspace (dim=%d)", dim);
+        return PB200_ERR_UNSUPPORTED;
+    }
+    const size_t need = pb200_lsh_encode_tc_workspace_bytes(n, dim, nbits);
+    if (workspace_bytes < need) {
+        set_error("lsh_encode_tc: workspace %zu B < required %zu B", workspace_bytes, need);
+        return PB200_ERR_WORKSPACE;
+    }
+    char* ws = static_cast<char*>(workspace);
+    float* proj_r = reinterpret_cast<float*>(ws);
+    float* y = reinterpret_cast<float*>(ws + align_up((size_t)nbits * dim * 4, 256));
+    unsigned int* astats = reinterpret_cast<unsigned int*>(ws + need - 256);   // [0] max |a~ - a|, [1] max |a~|
+    PB_CUDA(cudaMemsetAsync(astats, 0, 256, stream));
+    tcs::round_rows_kernel<<<(unsigned)ceil_div(nbits, 8), 256, 0, stream>>>(proj, proj_r, nbits, dim, nullptr, astats);
+    int rc = check_launch("round_rows_kernel");
+    if (rc) return rc;
+    for (int bit0 = 0; bit0 < nbits; bit0 += 256) {
+        const int nb = nbits - bit0 < 256 ? nbits - bit0 : 256;
+        DenseParams p{};
+        p.a1 = x; p.k1 = dim; p.a2 = nullptr; p.k2 = 0; p.pool_x = nullptr;
+        p.lists = ListArgs{nullptr, nullptr, nullptr, nullptr, 1, 0, 0};
+        p.w = proj_r + (size_t)bit0 * dim; p.bias = nullptr; p.ln_gamma = nullptr; p.ln_beta = nullptr;
+        p.n = n; p.n_out = nb; p.flags = 0; p.out = y;
+        if (!gather_dense_tf32_supported(p)) {
+            set_error("lsh_encode_tc: projection shape not covered by the tensor-core kernel (dim=%d)", dim);
+            return PB200_ERR_UNSUPPORTED;
+        }
+        rc = gather_dense_tf32(p, stream);
+        if (rc) return rc;
+        tcs::lsh_pack_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, stream>>>(x, n, dim, proj, nbits, bit0, nb, y, astats,
+                                                                         codes);
+        rc = check_launch("lsh_pack_kernel");
+        if (rc) return rc;
+    }
     return PB200_OK;
 }

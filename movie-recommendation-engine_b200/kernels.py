@@ -321,13 +321,27 @@ def topk_merge(scores, ids, k, largest):
     return out_s, out_i
 
 
-def lsh_encode(x, proj, return_projection=False):
+def lsh_encode(x, proj, return_projection=False, precision="auto"):
+    """Sign-random-projection codes.  precision: "fp32" = CUDA-core projection (pb200_lsh_encode);
+    "tc" = tensor-core projection + exact fp32 recompute of the projections near zero
+    (pb200_lsh_encode_tc, bit-identical codes); "auto" = "tc" for >= 256 vectors when covered."""
     dev = N.device_of(x, proj)
     x = N.dev_tensor(x, torch.float32, dev)
     proj = N.dev_tensor(proj, torch.float32, dev)
     n, d = x.shape
     nbits = proj.size(0)
+    if precision not in ("auto", "fp32", "tc"):
+        raise ValueError(f"precision must be 'auto', 'fp32' or 'tc', got {precision!r}")
     codes = torch.empty((n, nbits // 8), dtype=torch.uint8, device=dev)
+    ok = d % 4 == 0 and x.data_ptr() % 16 == 0 and proj.data_ptr() % 16 == 0 and not return_projection
+    if precision == "tc" and not ok:
+        raise N.NativeError("lsh_encode: precision='tc' needs dim % 4 == 0 and no projection output")
+    if ok and (precision == "tc" or (precision == "auto" and n >= TOPK_TC_MIN_QUERIES)):
+        ws_bytes = lib().pb200_lsh_encode_tc_workspace_bytes(n, d, nbits)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        check(lib().pb200_lsh_encode_tc(ptr(x), n, d, ptr(proj), nbits, ptr(codes), ptr(ws), ws_bytes,
+                                        stream_ptr(dev)), "lsh_encode_tc")
+        return codes
     y = torch.empty((n, nbits), dtype=torch.float32, device=dev) if return_projection else None
     check(lib().pb200_lsh_encode(ptr(x), n, d, ptr(proj), nbits, ptr(codes), ptr(y),
                                  stream_ptr(dev)), "lsh_encode")

@@ -282,3 +282,17 @@ def test_ivf_search_tensor_core_equals_list_scan(K, n, d, nlist, nq, k):
     np.testing.assert_array_equal(i1.cpu().numpy(), i0.cpu().numpy())
     np.testing.assert_array_equal(d1.cpu().numpy(), d0.cpu().numpy())
     assert int(st["list_scan_reruns"].item()) < nq // 2
+
+
+@pytest.mark.parametrize("n,d,nbits", [(5000, 128, 256), (300, 64, 64), (1000, 32, 512), (257, 100, 96)])
+def test_lsh_encode_tensor_core_bit_identical(K, n, d, nbits):
+    """pb200_lsh_encode_tc == pb200_lsh_encode bit for bit (projections near zero are recomputed in
+    fp32); rows of zeros and tiny vectors exercise the all-uncertain case."""
+    x = _data(n, d, 31)
+    x[7] = 0.0
+    x[11] *= 1e-20
+    proj = _data(nbits, d, 32, normalise=False)
+    xd, pd = torch.from_numpy(x).cuda(), torch.from_numpy(proj).cuda()
+    c1 = K.lsh_encode(xd, pd, precision="tc")
+    c0 = K.lsh_encode(xd, pd, precision="fp32")
+    np.testing.assert_array_equal(c1.cpu().numpy(), c0.cpu().numpy())
