@@ -257,6 +257,16 @@ int pb200_topk_tc(const float* queries, int64_t nq, const float* items, int64_t 
                   int32_t* out_ids, void* workspace, size_t workspace_bytes, int32_t* stats_out,
                   pb200_stream_t stream);
 
+/* N2: rank of a ground-truth item in the descending similarity order of a
+ * query item -- what calculate_hit_rate (utils/evaluation.py:5-36: rank <= k) and calculate_mrr
+ * (:38-73: 1 / (rank / scale)) derive from their per-pair matmul + topk / sort.
+ * out_rank[p] = 1 + #{j : s_j > s_gt or (s_j == s_gt and j < gt)}, s_j = <e[query_ids[p]], e[j]>
+ * (fp32, the query itself is NOT excluded, like the reference).  ids must be in [0, n). */
+size_t pb200_rank_of_target_workspace_bytes(int64_t num_pairs);
+int pb200_rank_of_target(const float* embeddings, int64_t n, int dim, const int32_t* query_ids,
+                         const int32_t* target_ids, int64_t num_pairs, int32_t* out_rank,
+                         void* workspace, size_t workspace_bytes, pb200_stream_t stream);
+
 /* Merge of per-shard candidate lists (multi-GPU: after the NCCL all-gather).
  * scores float32 [nq,c], ids int32 [nq,c] (id < 0 = padding); largest != 0 for IP. */
 int pb200_topk_merge(const float* scores, const int32_t* ids, int64_t nq, int c, int k,

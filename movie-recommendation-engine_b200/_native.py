@@ -63,6 +63,8 @@ SIGNATURES = {
     "pb200_topk_tc_workspace_bytes": (c_size, [c_i64, c_i64, c_int, c_int]),
     "pb200_topk_tc": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i32, c_ptr,
                               c_ptr, c_ptr, c_size, c_ptr, c_ptr]),
+    "pb200_rank_of_target_workspace_bytes": (c_size, [c_i64]),
+    "pb200_rank_of_target": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
     "pb200_topk_merge": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "pb200_lsh_encode": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "pb200_hamming_topk": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_i32, c_ptr, c_ptr,

@@ -198,6 +198,89 @@ static int choose_splits(int64_t nq, int64_t nx) {
     return (int)(s < 1 ? 1 : s);
 }
 
+// ---- N2: rank of a target item (hit-rate@k / MRR, utils/evaluation.py:5-73) ----
+// rank[p] = 1 + #{j : s_j > s_gt  or  (s_j == s_gt and j < gt)},  s_j = <e[q_p], e[j]>, the
+// position of the ground truth in the reference's descending sort.  tau is computed with the
+// tile kernel's own arithmetic (sequential fmaf over d), so column gt compares equal to it.
+__global__ void rank_tau_kernel(const float* __restrict__ e, int d, const int32_t* __restrict__ qid,
+                                const int32_t* __restrict__ gid, int64_t np, float* tau, int32_t* rank) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += (int64_t)gridDim.x * blockDim.x) {
+        const float* a = e + (int64_t)qid[p] * d;
+        const float* b = e + (int64_t)gid[p] * d;
+        float acc = 0.f;
+        for (int k = 0; k < d; ++k) acc = fmaf(__ldg(a + k), __ldg(b + k), acc);
+        tau[p] = acc;
+        rank[p] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) rank_count_kernel(const float* __restrict__ e, int64_t n, int d,
+                                                         const int32_t* __restrict__ qid,
+                                                         const int32_t* __restrict__ gid, int64_t np,
+                                                         const float* __restrict__ tau, int64_t split_len,
+                                                         int32_t* rank) {
+    __shared__ __align__(16) float q_s[TK][TQ + 4];
+    __shared__ __align__(16) float x_s[TK][TX + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int64_t p0 = (int64_t)blockIdx.x * TQ;
+    const int64_t xs = (int64_t)blockIdx.y * split_len, xe = min(n, xs + split_len);
+    float t[4]; int g[4]; int cnt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t p = p0 + ty * 4 + i;
+        t[i] = p < np ? tau[p] : INFINITY;
+        g[i] = p < np ? gid[p] : -1;
+        cnt[i] = 0;
+    }
+    for (int64_t x0 = xs; x0 < xe; x0 += TX) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < d; k0 += TK) {
+            {
+                const int r = tid >> 2, kk = (tid & 3) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kc = k0 + kk + i;
+                    const int64_t p = p0 + r, xi = x0 + r;
+                    q_s[kk + i][r] = (p < np && kc < d) ? __ldg(e + (int64_t)qid[p] * d + kc) : 0.f;
+                    x_s[kk + i][r] = (xi < xe && kc < d) ? __ldg(e + xi * d + kc) : 0.f;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < TK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(&q_s[kk][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&x_s[kk][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t xi = x0 + tx * 4 + j;
+                const float s = acc[i][j];
+                cnt[i] += (xi < xe) && (s > t[i] || (s == t[i] && (int)xi < g[i]));
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = cnt[i];
+        for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);   // the 16 threads of a row
+        const int64_t p = p0 + ty * 4 + i;
+        if (tx == 0 && p < np && c) atomicAdd(rank + p, c);
+    }
+}
+
 int topk_merge_run(const float* vals, const int32_t* ids, int64_t nq, int c, int vals_are_bad, int largest,
                    int k, float* out_scores, int32_t* out_ids, const int32_t* qsel,
                    const int32_t* qsel_count, int64_t qsel_base, cudaStream_t stream) {
@@ -312,4 +395,32 @@ extern "C" int pb200_topk_merge(const float* scores, const int32_t* ids, int64_t
         if (rc) return rc;
     }
     return PB200_OK;
+}
+
+extern "C" size_t pb200_rank_of_target_workspace_bytes(int64_t num_pairs) {
+    return align_up((size_t)(num_pairs > 0 ? num_pairs : 1) * 4, 256);
+}
+
+extern "C" int pb200_rank_of_target(const float* embeddings, int64_t n, int dim, const int32_t* query_ids,
+                                    const int32_t* target_ids, int64_t num_pairs, int32_t* out_rank,
+                                    void* workspace, size_t workspace_bytes, pb200_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PB_REQUIRE(n > 0 && dim > 0 && num_pairs >= 0 && n < 2147483647ll, "rank_of_target: bad sizes");
+    if (num_pairs == 0) return PB200_OK;
+    PB_REQUIRE(embeddings && query_ids && target_ids && out_rank && workspace, "rank_of_target: null pointer");
+    if (workspace_bytes < pb200_rank_of_target_workspace_bytes(num_pairs)) {
+        set_error("rank_of_target: workspace too small");
+        return PB200_ERR_WORKSPACE;
+    }
+    float* tau = static_cast<float*>(workspace);
+    const int64_t tb = ceil_div(num_pairs, 256) < kSMs * 8 ? ceil_div(num_pairs, 256) : kSMs * 8;
+    rank_tau_kernel<<<(unsigned)tb, 256, 0, stream>>>(embeddings, dim, query_ids, target_ids, num_pairs, tau, out_rank);
+    int rc = check_launch("rank_tau_kernel");
+    if (rc) return rc;
+    const int splits = choose_splits(num_pairs, n);
+    const int64_t split_len = ceil_div(ceil_div(n, splits), TX) * TX;
+    dim3 grid((unsigned)ceil_div(num_pairs, TQ), splits);
+    rank_count_kernel<<<grid, 256, 0, stream>>>(embeddings, n, dim, query_ids, target_ids, num_pairs, tau, split_len,
+                                                out_rank);
+    return check_launch("rank_count_kernel");
 }

@@ -309,6 +309,22 @@ def topk(queries, items, k, metric, exclude_ids=None, id_offset=0, precision="au
     return scores, ids
 
 
+def rank_of_target(embeddings, query_ids, target_ids):
+    """1-based rank of target_ids[p] in the descending similarity order of query_ids[p] (int32 [P])."""
+    dev = N.device_of(embeddings)
+    e = N.dev_tensor(embeddings, torch.float32, dev)
+    q = N.dev_tensor(query_ids, torch.int32, dev).reshape(-1)
+    g = N.dev_tensor(target_ids, torch.int32, dev).reshape(-1)
+    if q.numel() != g.numel():
+        raise RuntimeError("query and ground-truth index lists differ in length")
+    rank = torch.empty(q.numel(), dtype=torch.int32, device=dev)
+    ws_bytes = lib().pb200_rank_of_target_workspace_bytes(q.numel())
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    check(lib().pb200_rank_of_target(ptr(e), e.size(0), e.size(1), ptr(q), ptr(g), q.numel(), ptr(rank), ptr(ws),
+                                     ws_bytes, stream_ptr(dev)), "rank_of_target")
+    return rank
+
+
 def topk_merge(scores, ids, k, largest):
     dev = N.device_of(scores)
     s = N.dev_tensor(scores, torch.float32, dev)

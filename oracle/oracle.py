@@ -438,6 +438,32 @@ def exact_ip(emb, queries, k, exclude=None):
     return topk_total_order(sim, k, largest=True)
 
 
+def rank_of_target(emb, query_ids, target_ids):
+    """Rank (1-based) of the ground-truth item in the descending similarity order of
+    utils/evaluation.py:24-33 (hit-rate: rank <= k) and :56-66 (MRR: np.where(sorted == gt)).
+    Ties (measure zero on real embeddings): items with an equal score and a smaller index
+    come first -- the order a stable descending sort gives."""
+    e = np.asarray(emb, np.float32)
+    q = np.asarray(query_ids, np.int64)
+    g = np.asarray(target_ids, np.int64)
+    sim = e[q] @ e.T
+    s_gt = sim[np.arange(len(q)), g]
+    above = (sim > s_gt[:, None]).sum(1)
+    ties = ((sim == s_gt[:, None]) & (np.arange(e.shape[0])[None, :] < g[:, None])).sum(1)
+    return (1 + above + ties).astype(np.int64)
+
+
+def hit_rate(emb, query_ids, target_ids, k):
+    """utils/evaluation.py:5-36."""
+    return float((rank_of_target(emb, query_ids, target_ids) <= k).sum() / len(query_ids))
+
+
+def mrr(emb, query_ids, target_ids, scale=100):
+    """utils/evaluation.py:38-73: mean of 1 / (rank / scale)."""
+    r = rank_of_target(emb, query_ids, target_ids)
+    return float(np.mean([1.0 / (int(x) / scale) for x in r]))
+
+
 def exact_l2(emb, queries, k):
     """faiss IndexFlatL2.search as used at utils/nearest_neighbors.py:174-181:
     squared L2 via ||x||^2 + ||y||^2 - 2<x,y>, clipped at 0, ascending.  UNPINNED."""

@@ -10,6 +10,7 @@ Fixtures (all small, seeded):
   pooling.npz      P1-P5 on ragged lists (empty, out-of-range, zero-sum, bare int)
   forward.npz      G1, G2, G4 (importance + MLP branches, get_embeddings), G3
   exact.npz        E1 generate_recommendations
+  evaluation.npz   N2 calculate_hit_rate / calculate_mrr / evaluate_embeddings (8(f) "next" row)
 """
 import json
 import os
@@ -209,8 +210,28 @@ def make_exact():
     print("exact.npz", ids.shape)
 
 
+def make_evaluation():
+    g = torch.Generator().manual_seed(13)
+    emb = torch.nn.functional.normalize(torch.randn(700, 32, generator=g), dim=1)
+    pairs = torch.stack([torch.randint(0, 700, (300,), generator=g), torch.randint(0, 700, (300,), generator=g)], 1)
+    q, gt = pairs[:, 0].numpy(), pairs[:, 1].numpy()
+    ks = [1, 10, 50, 100, 500]
+    hr = np.array([ev.calculate_hit_rate(emb, q, gt, k=k) for k in ks])
+    m = ev.calculate_mrr(emb, q, gt)
+    m7 = ev.calculate_mrr(emb, q, gt, scale=7)
+    res = ev.evaluate_embeddings(emb, {"positive_pairs": pairs})
+    # ranks as the reference's MRR loop sees them (torch.sort descending, first match)
+    ranks = np.array([int(np.where(torch.sort(emb[a] @ emb.t(), descending=True)[1].numpy() == b)[0][0]) + 1
+                      for a, b in zip(q, gt)])
+    np.savez_compressed(os.path.join(OUT, "evaluation.npz"), emb=emb.numpy(), pairs=pairs.numpy(), ks=np.array(ks),
+                        hit_rates=hr, mrr=m, mrr_scale7=m7, ranks=ranks,
+                        evaluate=json.dumps({k: float(v) for k, v in res.items()}))
+    print("evaluation.npz", hr, m)
+
+
 if __name__ == "__main__":
     make_walks()
     make_pooling()
     make_forward()
     make_exact()
+    make_evaluation()

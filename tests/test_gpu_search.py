@@ -296,3 +296,50 @@ def test_lsh_encode_tensor_core_bit_identical(K, n, d, nbits):
     c1 = K.lsh_encode(xd, pd, precision="tc")
     c0 = K.lsh_encode(xd, pd, precision="fp32")
     np.testing.assert_array_equal(c1.cpu().numpy(), c0.cpu().numpy())
+
+
+# ---- N2: hit-rate / MRR through the rank kernel (SURVEY 8(f) "next" row) -------------------------
+def test_hit_rate_mrr_vs_reference_golden(K):
+    import json
+    from mre_b200.utils.evaluation import calculate_hit_rate, calculate_mrr, evaluate_embeddings
+    g = Hh.load("evaluation.npz")
+    emb = torch.from_numpy(g["emb"])
+    q, gt = g["pairs"][:, 0], g["pairs"][:, 1]
+    ranks = K.rank_of_target(emb.cuda(), torch.from_numpy(q), torch.from_numpy(gt)).cpu().numpy()
+    np.testing.assert_array_equal(ranks, g["ranks"])
+    for k, want in zip(g["ks"], g["hit_rates"]):
+        assert calculate_hit_rate(emb, q, gt, k=int(k)) == want
+    assert abs(calculate_mrr(emb, q, gt) - float(g["mrr"])) < 1e-12
+    assert abs(calculate_mrr(emb.cuda(), list(q), list(gt), scale=7) - float(g["mrr_scale7"])) < 1e-12
+    ev = evaluate_embeddings(emb, {"positive_pairs": torch.from_numpy(g["pairs"])})
+    want = json.loads(str(g["evaluate"]))
+    assert set(ev) == set(want)
+    for key in want:
+        assert abs(ev[key] - want[key]) < 1e-12
+    with pytest.raises(RuntimeError):
+        calculate_hit_rate(emb, q, gt, k=701)
+
+
+def test_rank_of_target_ties_edges_and_size(K):
+    """Duplicates (tie rule: equal score, smaller index first), a pair whose target is the query,
+    non-multiple-of-tile sizes; and a C3-sized run checked against the exact search kernel:
+    rank <= 10  <=>  the target is in the query's top-10 (query not excluded)."""
+    from mre_b200 import _native as N
+    x = _data(1000, 48, 41)
+    x[10] = x[3]; x[500] = x[3]
+    q = np.array([3, 3, 3, 10, 999, 0, 77], dtype=np.int64)
+    gt = np.array([3, 10, 500, 3, 0, 999, 77], dtype=np.int64)
+    got = K.rank_of_target(torch.from_numpy(x).cuda(), torch.from_numpy(q), torch.from_numpy(gt)).cpu().numpy()
+    np.testing.assert_array_equal(got, O.rank_of_target(x, q, gt))
+    from mre_b200 import synthetic as S
+    e = S.spread_embeddings(62423, 128, seed=1).cuda().contiguous()
+    gen = torch.Generator().manual_seed(3)
+    qq = torch.randint(0, 62423, (4096,), generator=gen)
+    _s, ids = K.topk(e[qq.cuda()].contiguous(), e, 10, N.METRIC_IP, precision="fp32")
+    tgt = ids[torch.arange(4096), torch.randint(0, 10, (4096,), generator=gen)].cpu()      # a top-10 member
+    far = torch.randint(0, 62423, (4096,), generator=gen)
+    r_in = K.rank_of_target(e, qq, tgt).cpu()
+    r_far = K.rank_of_target(e, qq, far).cpu()
+    assert bool((r_in <= 10).all())
+    in_top = (ids.cpu() == far[:, None].to(torch.int32)).any(1)
+    assert bool(((r_far <= 10) == in_top).all())

@@ -129,3 +129,18 @@ def test_unpinned_restatements_self_consistent():
     np.testing.assert_allclose(ds, d2, atol=1e-5)
     s, i = O.topk_merge([ds[:, :2], ds[:, 2:]], [ii[:, :2], ii[:, 2:]], 4, largest=False)
     np.testing.assert_array_equal(i, ii)
+
+
+def test_rank_metrics_match_reference():
+    """N2: the oracle's rank restatement reproduces the reference's hit-rate@k, MRR
+    and evaluate_embeddings (utils/evaluation.py:5-104) on the committed fixture."""
+    import json
+    g = Hh.load("evaluation.npz")
+    q, gt = g["pairs"][:, 0], g["pairs"][:, 1]
+    np.testing.assert_array_equal(O.rank_of_target(g["emb"], q, gt), g["ranks"])
+    for k, want in zip(g["ks"], g["hit_rates"]):
+        assert O.hit_rate(g["emb"], q, gt, int(k)) == want
+    assert abs(O.mrr(g["emb"], q, gt) - float(g["mrr"])) < 1e-12
+    assert abs(O.mrr(g["emb"], q, gt, scale=7) - float(g["mrr_scale7"])) < 1e-12
+    ev = json.loads(str(g["evaluate"]))
+    assert ev["hit_rate@10"] == O.hit_rate(g["emb"], q, gt, 10) and abs(ev["mrr"] - float(g["mrr"])) < 1e-12
