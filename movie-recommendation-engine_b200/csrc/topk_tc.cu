@@ -71,6 +71,15 @@ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t col
     return ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xFFFFFFFFu - col);
 }
 
+// optional cycle accounting of one scan warp (make EXTRA=-DPB200_SEARCH_PROFILE)
+#ifdef PB200_SEARCH_PROFILE
+#define SP_NOW() clock64()
+#define SP_ADD(var, t0) (var) += clock64() - (t0)
+#else
+#define SP_NOW() 0ll
+#define SP_ADD(var, t0) do { } while (0)
+#endif
+
 enum { kBarFull = 0, kBarEmpty = kMaxStages, kBarAFull = 2 * kMaxStages, kBarAFree, kBarTFull,
        kBarTEmpty = kBarTFull + 2, kNumBars = kBarTEmpty + 2 };
 
@@ -260,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
         const int ks = p.ks;
         unsigned long long* wl = lists + (size_t)row0 * ks;  // row r of the warp: wl[r * ks + rank]
         int tc_ = 0;
+        long long sp_wait = 0, sp_ld = 0, sp_fast = 0, sp_slow = 0, sp_groups = 0, sp_slowg = 0, sp_t0 = SP_NOW();
         for (int64_t t = t_begin; t < t_end;) {
             const Seg sg = segment(t);
             t = sg.t_next;
@@ -282,14 +292,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
                     elig = l >= 0 && ((w >> (l & 31)) & 1u);
                 }
                 float thr_t = elig ? thr : INFINITY;
+                const long long w0 = SP_NOW();
                 mbar_wait(bar(kBarTFull + b), (uint32_t)(ub & 1));
+                SP_ADD(sp_wait, w0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                        (uint32_t)((b * qt + qi) * kTileN);
 #pragma unroll 1
                 for (int cb = 0; cb < kTileN / 32; ++cb) {
                     uint32_t v[32];
+                    const long long l0 = SP_NOW();
                     tmem_ld32(taddr + (uint32_t)(cb * 32), v);
+                    SP_ADD(sp_ld, l0);
                     if (cb == kTileN / 32 - 1) {   // accumulator fully read: hand it back
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         mbar_arrive(bar(kBarTEmpty + b));
@@ -308,22 +322,42 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
                         }
+                        const long long g0 = SP_NOW();
                         const float gm = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])),
                                                fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
-                        if (__any_sync(kFull, gm >= thr_t)) {
+                        const bool slowp = __any_sync(kFull, gm >= thr_t);
+                        SP_ADD(sp_fast, g0);
+                        sp_groups += 1;
+                        if (slowp) {
+                            const long long s0 = SP_NOW();
+                            sp_slowg += 1;
+                            // all 8 votes first, against the threshold at the start of the group: a vote
+                            // that waits for the previous column's insertion would serialise eight
+                            // ~30-cycle round trips; a candidate that a later insertion has outdated
+                            // is simply rejected by insert_column (position = ks).  (Merging the
+                            // candidates of all 8 columns into 4-row batches was slower: 5.46 vs 4.88 ms.)
+                            unsigned m8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                m8[i] = __ballot_sync(kFull, f[i] >= thr_t && col0 + g * 8 + i < n_end);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const int col = col0 + g * 8 + i;
-                                const unsigned m = __ballot_sync(kFull, f[i] >= thr_t && col < n_end);
-                                if (m) {
-                                    thr = insert_column(m, f[i], 0xFFFFFFFFu - (uint32_t)col, wl, ks, lane, thr);
+                                if (m8[i]) {
+                                    thr = insert_column(m8[i], f[i], 0xFFFFFFFFu - (uint32_t)(col0 + g * 8 + i), wl, ks,
+                                                        lane, thr);
                                     thr_t = elig ? thr : INFINITY;
                                 }
                             }
+                            SP_ADD(sp_slow, s0);
                         }
                     }
                 }
             }
+#ifdef PB200_SEARCH_PROFILE
+            if (t >= t_end && lane == 0 && blockIdx.x == 3)
+                printf("scan warp %d: total %lld  wait_tfull %lld  tmem_ld %lld  fast %lld  slow %lld  groups %lld  slow_groups %lld\n",
+                       e, (long long)(clock64() - sp_t0), sp_wait, sp_ld, sp_fast, sp_slow, sp_groups, sp_slowg);
+#endif
             // segment done: every row's sorted list -> short_keys[sp][q][0..ks)
             __syncwarp();
             for (int r = 0; r < 32; ++r) {
@@ -352,11 +386,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const S
 __global__ void __launch_bounds__(256) round_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                          int64_t n, int d, float* __restrict__ resid,
                                                          unsigned int* max_bits) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n) return;
+    __shared__ float s_r[8], s_n[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     float r2 = 0.f, n2 = 0.f;
-    for (int c = lane * 4; c < d; c += 128) {
+    for (int c = lane * 4; row < n && c < d; c += 128) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(in + row * d + c));
         float4 o;
         o.x = __uint_as_float(to_tf32(v.x)); o.y = __uint_as_float(to_tf32(v.y));
@@ -370,13 +404,18 @@ __global__ void __launch_bounds__(256) round_rows_kernel(const float* __restrict
         r2 += __shfl_xor_sync(kFull, r2, o);
         n2 += __shfl_xor_sync(kFull, n2, o);
     }
+    const float r = sqrtf(r2) * 1.0001f, nn = sqrtf(n2) * 1.0001f;   // cover the fp32 rounding of the sums
     if (lane == 0) {
-        const float r = sqrtf(r2) * 1.0001f, nn = sqrtf(n2) * 1.0001f;   // cover the fp32 rounding of the sums
-        if (resid) resid[row] = r;
-        if (max_bits) {
-            if (r == r) atomicMax(max_bits, __float_as_uint(r));
-            if (nn == nn) atomicMax(max_bits + 1, __float_as_uint(nn));
-        }
+        if (resid && row < n) resid[row] = r;
+        s_r[warp] = (row < n && r == r) ? r : 0.f;
+        s_n[warp] = (row < n && nn == nn) ? nn : 0.f;
+    }
+    __syncthreads();
+    if (max_bits && threadIdx.x == 0) {          // one atomic pair per block, not per row
+        float mr = 0.f, mn = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { mr = fmaxf(mr, s_r[w]); mn = fmaxf(mn, s_n[w]); }
+        if (mr > 0.f) atomicMax(max_bits, __float_as_uint(mr));
+        if (mn > 0.f) atomicMax(max_bits + 1, __float_as_uint(mn));
     }
 }
 
