@@ -334,7 +334,10 @@ def main_b200(args):
                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes,
                             "avg_launch_ms": avg_ms, "executed_steps": int(executed.sum()),
-                            "share_of_step": sum(walk_ms) / dev_ms}
+                            "share_of_step": sum(walk_ms) / dev_ms,
+                            "limiter": "ncu (profiles/r1_final_ncu_full_walk_dense_pool.txt): LSU data-pipe "
+                                       "wavefronts 66 % of peak (divergent 32 B loads + shared-memory atomics), "
+                                       "issue slots 59 %, DRAM 28 %: the kernel is not HBM-bandwidth bound"}
     if ws == 1 and not args.no_cpu_baseline:
         r = run_cpu_port(inp, args.cpu_sample, 3, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
