@@ -119,8 +119,8 @@ __device__ __noinline__ float insert_column(unsigned m, float fi, uint32_t klo, 
     return thr;
 }
 
-template <int kMetric, int kCtasPerSm>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) search_tc_kernel(const SearchParams p,
+template <int kMetric>
+__global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchParams p,
                                                                 const __grid_constant__ CUtensorMap tm_q,
                                                                 const __grid_constant__ CUtensorMap tm_x) {
     extern __shared__ uint8_t smem_raw[];
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
 
 // ---- host side ----
 struct Plan {
-    int qt = 0, nchunks = 0, ks = 0, splits = 0, stages = 0, grid = 0, fsplits = 0, fsplits0 = 0, ctas_per_sm = 1, align_slack = 1024;
+    int qt = 0, nchunks = 0, ks = 0, splits = 0, stages = 0, grid = 0, fsplits = 0, fsplits0 = 0, align_slack = 1024;
     int64_t split_len, nx_pad, cap_f, cap_f0;
     size_t smem_bytes;
     // workspace offsets
@@ -556,21 +556,15 @@ static int env_int(const char* name, int dflt) {
 
 // kernel geometry for nq x nx scores with `nchunks` 128-byte K chunks per row and lists of p.ks
 static bool make_geometry(int64_t nq, int64_t nx, Plan& p) {
-    // Two configurations (PB200_TOPK_TC_CTAS): 1 CTA/SM with two resident query tiles (halves the
-    // L2 -> SM item traffic; default), or 2 CTAs/SM with one tile each (twice the scan warps per
-    // SM; measured slower: 4.99 vs 4.28 ms at C3).
-    p.ctas_per_sm = env_int("PB200_TOPK_TC_CTAS", 1) == 2 ? 2 : 1;
+    // Two resident query tiles per CTA halve the L2 -> SM item traffic; needs room for the operands,
+    // the sorted lists and >= 3 ring stages.  (2 CTAs/SM with one tile each -- twice the scan warps --
+    // was measured slower, 4.99 vs 4.28 ms at C3, and removed.)
     p.align_slack = 1024;
     auto fixed_bytes = [&](int qt) {
         return (size_t)qt * p.nchunks * kABytes + (size_t)p.ks * qt * kTileM * 8 + kNumBars * 8 + 16;
     };
-    size_t budget = 225 * 1024;
-    if (p.ctas_per_sm == 2) {
-        budget = 115712;   // (228 KB - 2 x 1 KB reserved) / 2
-        p.align_slack = 1024 - 160;   // the window is 1 KB aligned in practice; the kernel checks
-        if (fixed_bytes(1) + p.align_slack + 2 * (size_t)kNBytes > budget) { p.ctas_per_sm = 1; budget = 225 * 1024; p.align_slack = 1024; }
-    }
-    p.qt = (p.ctas_per_sm == 1 && nq > 128 && fixed_bytes(2) + 1024 + 3 * (size_t)kNBytes <= budget) ? 2 : 1;
+    const size_t budget = 225 * 1024;
+    p.qt = (nq > 128 && fixed_bytes(2) + 1024 + 3 * (size_t)kNBytes <= budget) ? 2 : 1;
     const size_t fixed = fixed_bytes(p.qt) + p.align_slack;
     if (fixed + 2 * (size_t)kNBytes > budget) return false;
     int st = (int)((budget - fixed) / kNBytes);
@@ -588,7 +582,7 @@ static bool make_geometry(int64_t nq, int64_t nx, Plan& p) {
     p.split_len = ceil_div(ceil_div(nx, chunks), kTileN) * kTileN;
     p.splits = (int)ceil_div(nx, p.split_len);          // no empty chunk
     const int64_t total_sub = qgroups * p.splits;
-    p.grid = (int)(total_sub < kSMs * p.ctas_per_sm ? total_sub : kSMs * p.ctas_per_sm);
+    p.grid = (int)(total_sub < kSMs ? total_sub : kSMs);
     return true;
 }
 
@@ -711,18 +705,15 @@ extern "C" int pb200_topk_tc(const float* queries, int64_t nq, const float* item
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + pl.off_short);
     // slots no segment starts at stay empty (0)
     PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
-#define PB_LAUNCH_SEARCH(M_, C_)                                                                        \
-    do {                                                                                               \
-        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<M_, C_>,                                    \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)); \
-        tcs::search_tc_kernel<M_, C_><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x); \
-    } while (0)
     if (metric == PB200_METRIC_IP) {
-        if (pl.ctas_per_sm == 2) PB_LAUNCH_SEARCH(PB200_METRIC_IP, 2); else PB_LAUNCH_SEARCH(PB200_METRIC_IP, 1);
+        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_IP>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        tcs::search_tc_kernel<PB200_METRIC_IP><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
     } else {
-        if (pl.ctas_per_sm == 2) PB_LAUNCH_SEARCH(PB200_METRIC_L2, 2); else PB_LAUNCH_SEARCH(PB200_METRIC_L2, 1);
+        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_L2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        tcs::search_tc_kernel<PB200_METRIC_L2><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
     }
-#undef PB_LAUNCH_SEARCH
     rc = check_launch("search_tc_kernel");
     if (rc) return rc;
 
@@ -889,15 +880,9 @@ extern "C" int pb200_hamming_topk_tc(const uint8_t* codes_q, int64_t nq, const u
     sp.kind = 1; sp.hx = nullptr;
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + h.off_short);
     PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
-    if (pl.ctas_per_sm == 2) {
-        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_IP, 2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        tcs::search_tc_kernel<PB200_METRIC_IP, 2><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
-    } else {
-        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_IP, 1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        tcs::search_tc_kernel<PB200_METRIC_IP, 1><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
-    }
+    PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_IP>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    tcs::search_tc_kernel<PB200_METRIC_IP><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
     int rc = check_launch("search_tc_kernel");
     if (rc) return rc;
     tcs::hamming_finish_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(
@@ -1025,15 +1010,9 @@ extern "C" int pb200_ivf_search_tc(const float* queries, int64_t nq, int dim, co
     sp.kind = 0; sp.hx = hxp; sp.tile_list = tile_list; sp.pmask = reinterpret_cast<const uint32_t*>(pmask);
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + h.off_short);
     PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
-    if (pl.ctas_per_sm == 2) {
-        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_L2, 2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        tcs::search_tc_kernel<PB200_METRIC_L2, 2><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
-    } else {
-        PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_L2, 1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        tcs::search_tc_kernel<PB200_METRIC_L2, 1><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
-    }
+    PB_CUDA(cudaFuncSetAttribute(tcs::search_tc_kernel<PB200_METRIC_L2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    tcs::search_tc_kernel<PB200_METRIC_L2><<<pl.grid, tcs::kThreads, pl.smem_bytes, stream>>>(sp, tm_q, tm_x);
     rc = check_launch("search_tc_kernel");
     if (rc) return rc;
 
