@@ -104,6 +104,20 @@ int pb200_walk_index_sizes(const int64_t* row_ptr, int64_t num_nodes, int64_t* s
 int pb200_walk_index_build(const int64_t* row_ptr, const int32_t* col, const void* cum,
                            int64_t num_nodes, const void* workspace, uint32_t* meta, uint32_t* idx,
                            uint32_t* leaf, pb200_stream_t stream);
+
+/* Leaf formats of the sampling index.  WIDE: 64-byte blocks {8 x u32 cumulative weight, 8 x u32 id}.
+ * COMPACT: 32-byte blocks {8 x u8 (block separator - cumulative weight), 8 x u16 id low, 8 x u8 id
+ * high}: one 256-bit load per walk step instead of two and half the DRAM bytes; valid when
+ * num_nodes < 2^24 and pb200_walk_index_leaf_range reports <= 255 (leaf buffer: 32 bytes per
+ * leaf block instead of 64).  The selected edges are identical. */
+#define PB200_LEAF_WIDE 0
+#define PB200_LEAF_COMPACT 1
+/* max over all 8-edge leaf blocks of (last - first cumulative weight) -> *max_range_out (device u32) */
+int pb200_walk_index_leaf_range(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
+                                uint32_t* max_range_out, pb200_stream_t stream);
+int pb200_walk_index_build_ex(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                              int64_t num_nodes, const void* workspace, uint32_t* meta, uint32_t* idx,
+                              uint32_t* leaf, int leaf_format, pb200_stream_t stream);
 /* pb200_walk_topt on the sampling index (same outputs, bit-identical results). */
 int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx, const uint32_t* leaf,
                             int64_t num_nodes, const int32_t* starts, int64_t n, int num_walks,
@@ -117,11 +131,11 @@ int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx, const uin
  * as the last node of the graph plays the role of the advancing global RNG stream
  * (utils/random_walk.py:79; per-layer resampling at model/pinsage.py:271-275). */
 int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* idx, const uint32_t* leaf,
-                               int64_t num_nodes, const int32_t* starts, int64_t n, int num_walks,
-                               int walk_length, int num_neighbors, uint64_t seed, uint32_t epoch,
-                               const uint32_t* epoch_dev, int32_t* out_ids, int32_t* out_counts,
-                               float* out_weights, int32_t* out_nvalid, int32_t* trace_out,
-                               pb200_stream_t stream);
+                               int leaf_format, int64_t num_nodes, const int32_t* starts, int64_t n,
+                               int num_walks, int walk_length, int num_neighbors, uint64_t seed,
+                               uint32_t epoch, const uint32_t* epoch_dev, int32_t* out_ids,
+                               int32_t* out_counts, float* out_weights, int32_t* out_nvalid,
+                               int32_t* trace_out, pb200_stream_t stream);
 int pb200_u32_add(uint32_t* counter, uint32_t delta, pb200_stream_t stream);
 
 /* Counting stage alone, given traces (parity "given the same walk traces"):

@@ -37,7 +37,10 @@ SIGNATURES = {
     "pb200_walk_topt_indexed": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
                                         c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                         c_ptr]),
-    "pb200_walk_topt_indexed_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
+    "pb200_walk_index_leaf_range": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "pb200_walk_index_build_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                          c_ptr]),
+    "pb200_walk_topt_indexed_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_int,
                                            c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                            c_ptr]),
     "pb200_u32_add": (c_int, [c_ptr, c_u32, c_ptr]),
@@ -99,6 +102,7 @@ POOL_ROUND_TF32 = 0x100
 PREC_FP32, PREC_TF32, PREC_AUTO = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "auto": PREC_AUTO}
 METRIC_IP, METRIC_L2 = 0, 1
+LEAF_WIDE, LEAF_COMPACT = 0, 1          # sampling-index leaf formats (pb200_walk_index_build_ex)
 
 _lib = None
 

@@ -6,6 +6,11 @@
 // index turns a step into  meta -> [upper level(s)] -> leaf :
 //   meta  uint4 per node  {leaf block offset, degree, row total, upper-level block offset}
 //   leaf  64 B block      {8 cumulative weights (uint32, 0xFFFFFFFF padded), 8 neighbour ids}
+//         or, "compact" (PB200_LEAF_COMPACT: < 2^24 nodes and every block spans <= 255 weight
+//         quanta -- true for rating graphs), a 32 B block {8 x u8 (block separator - cum),
+//         8 x u16 id low halves, 8 x u8 id high bytes}: ONE 256-bit load per step instead of two
+//         (the walk kernel is bound by LSU wavefronts: one per lane and load) and half the
+//         DRAM bytes; the separator is the parent key that selected the block (or the row total)
 //   idx   32 B block      8 separator keys = last cumulative weight under each child block
 // Every node of the tree is one 256-bit load (LDG.E.256).  The upper levels take
 // ~E/7 * 4 B (about 30 MB at ML-25M scale) and stay L2-resident (evict_last), so a step costs
@@ -45,13 +50,34 @@ __global__ void widx_sizes_kernel(const uint32_t* leaf_off, const uint32_t* idx_
     }
 }
 
+// largest (last cum - first cum) over all 8-edge leaf blocks: decides whether the compact leaf fits
+__global__ void __launch_bounds__(256) widx_range_kernel(const int64_t* __restrict__ row_ptr,
+                                                         const uint32_t* __restrict__ cum, int64_t N,
+                                                         uint32_t* max_range) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t m = 0;
+    for (int64_t v = wid; v < N; v += nw) {
+        const int64_t r0 = row_ptr[v];
+        const uint32_t deg = (uint32_t)(row_ptr[v + 1] - r0);
+        const uint32_t nb0 = (deg + 7) >> 3;
+        for (uint32_t b = lane; b < nb0; b += 32) {
+            const uint32_t last = min(8u * b + 7u, deg - 1u);
+            m = max(m, cum[r0 + last] - cum[r0 + 8u * b]);
+        }
+    }
+    m = __reduce_max_sync(kFull, m);
+    if (lane == 0 && m) atomicMax(max_range, m);
+}
+
 // one warp per row: meta, leaf blocks, upper levels (top level first)
 __global__ void __launch_bounds__(256) widx_fill_kernel(const int64_t* __restrict__ row_ptr,
                                                         const int32_t* __restrict__ col,
                                                         const uint32_t* __restrict__ cum, int64_t N,
                                                         const uint32_t* __restrict__ leaf_off,
                                                         const uint32_t* __restrict__ idx_off,
-                                                        uint4* meta, uint32_t* idx, uint32_t* leaf) {
+                                                        uint4* meta, uint32_t* idx, uint32_t* leaf, int compact) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -65,9 +91,18 @@ __global__ void __launch_bounds__(256) widx_fill_kernel(const int64_t* __restric
         // leaves
         for (uint32_t i = lane; i < nb0 * 8; i += 32) {
             const uint32_t b = i >> 3, j = i & 7;
-            uint32_t* blk = leaf + ((size_t)lo + b) * 16;
-            blk[j] = i < deg ? cum[r0 + i] : 0xFFFFFFFFu;
-            blk[8 + j] = i < deg ? (uint32_t)col[r0 + i] : 0xFFFFFFFFu;
+            if (compact) {
+                uint8_t* blk = reinterpret_cast<uint8_t*>(leaf + ((size_t)lo + b) * 8);
+                const uint32_t sep = cum[r0 + min(8u * b + 7u, deg - 1u)];
+                const uint32_t id = i < deg ? (uint32_t)col[r0 + i] : 0xFFFFFFu;
+                blk[j] = i < deg ? (uint8_t)(sep - cum[r0 + i]) : (uint8_t)0;   // padding: never >= a positive threshold
+                reinterpret_cast<uint16_t*>(blk + 8)[j] = (uint16_t)(id & 0xFFFFu);
+                blk[24 + j] = (uint8_t)(id >> 16);
+            } else {
+                uint32_t* blk = leaf + ((size_t)lo + b) * 16;
+                blk[j] = i < deg ? cum[r0 + i] : 0xFFFFFFFFu;
+                blk[8 + j] = i < deg ? (uint32_t)col[r0 + i] : 0xFFFFFFFFu;
+            }
         }
         // upper levels: level l (>=1) has one key per block of level l-1; key j of level l is
         // the last cumulative weight covered by that block: cum[min(8^l (j+1), deg) - 1]
@@ -143,10 +178,25 @@ extern "C" int pb200_walk_index_sizes(const int64_t* row_ptr, int64_t num_nodes,
     return check_launch("widx_sizes_kernel");
 }
 
-extern "C" int pb200_walk_index_build(const int64_t* row_ptr, const int32_t* col, const void* cum,
-                                      int64_t num_nodes, const void* workspace, uint32_t* meta,
-                                      uint32_t* idx, uint32_t* leaf, pb200_stream_t stream) {
+extern "C" int pb200_walk_index_leaf_range(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
+                                           uint32_t* max_range_out, pb200_stream_t stream) {
+    PB_REQUIRE(num_nodes >= 0 && max_range_out, "walk_index_leaf_range: bad arguments");
+    PB_CUDA(cudaMemsetAsync(max_range_out, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    if (num_nodes == 0) return PB200_OK;
+    PB_REQUIRE(row_ptr && cum, "walk_index_leaf_range: null pointer");
+    const unsigned blocks = (unsigned)(ceil_div(num_nodes, 8) < kSMs * 16 ? ceil_div(num_nodes, 8) : kSMs * 16);
+    widx_range_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(row_ptr, static_cast<const uint32_t*>(cum), num_nodes,
+                                                               max_range_out);
+    return check_launch("widx_range_kernel");
+}
+
+extern "C" int pb200_walk_index_build_ex(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                                         int64_t num_nodes, const void* workspace, uint32_t* meta,
+                                         uint32_t* idx, uint32_t* leaf, int leaf_format, pb200_stream_t stream) {
     PB_REQUIRE(num_nodes >= 0, "walk_index_build: bad arguments");
+    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || leaf_format == PB200_LEAF_COMPACT, "walk_index_build: unknown leaf format");
+    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || num_nodes <= (1 << 24) - 1,
+               "walk_index_build: the compact leaf holds 24-bit node ids");
     if (num_nodes == 0) return PB200_OK;
     PB_REQUIRE(row_ptr && workspace && meta, "walk_index_build: null pointer");
     PB_REQUIRE(((uintptr_t)meta % 16 == 0) && ((uintptr_t)idx % 32 == 0) && ((uintptr_t)leaf % 64 == 0),
@@ -155,6 +205,13 @@ extern "C" int pb200_walk_index_build(const int64_t* row_ptr, const int32_t* col
     const unsigned blocks = (unsigned)(ceil_div(num_nodes, 8) < kSMs * 16 ? ceil_div(num_nodes, 8) : kSMs * 16);
     widx_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         row_ptr, col, static_cast<const uint32_t*>(cum), num_nodes, w.leaf_off, w.idx_off,
-        reinterpret_cast<uint4*>(meta), idx, leaf);
+        reinterpret_cast<uint4*>(meta), idx, leaf, leaf_format == PB200_LEAF_COMPACT);
     return check_launch("widx_fill_kernel");
+}
+
+extern "C" int pb200_walk_index_build(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                                      int64_t num_nodes, const void* workspace, uint32_t* meta,
+                                      uint32_t* idx, uint32_t* leaf, pb200_stream_t stream) {
+    return pb200_walk_index_build_ex(row_ptr, col, cum, num_nodes, workspace, meta, idx, leaf, PB200_LEAF_WIDE,
+                                     stream);
 }

@@ -32,6 +32,7 @@ struct WalkParams {
     const uint4* __restrict__ meta;        // indexed mode (walk_index.cu)
     const uint32_t* __restrict__ idx;
     const uint32_t* __restrict__ leaf;
+    int leaf_compact;                       // PB200_LEAF_COMPACT: 32-byte leaf blocks
     int64_t n;
     int64_t num_nodes;
     int W, L, T;
@@ -128,7 +129,7 @@ __device__ __forceinline__ uint32_t count_le(const U8& k, uint32_t t) {
 
 // Returns the next node (>= 0) or -1 at a dead end.  Same rule as pick_edge: first edge whose
 // cumulative weight exceeds t = floor(k53 * total / 2^53).
-template <bool kBin>
+template <bool kBin, bool kCompact>
 __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
                                             const uint32_t* __restrict__ idx,
                                             const uint32_t* __restrict__ leaf, int cur,
@@ -142,15 +143,38 @@ __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
     // top level first.  A real loop (the trip count is 1-2 for typical degrees).
     const uint32_t nb0 = (m.y + 7u) >> 3;
     uint32_t pos = 0;
+    uint32_t sep = m.z;                  // compact leaf: last cumulative weight of the chosen block
     if (nb0 > 1u) {
         int l = (((31 - __clz(nb0 - 1u)) * 11) >> 5) + 1;      // floor(log2(nb0-1)) / 3 + 1
         uint32_t off = m.w;
 #pragma unroll 1
         for (; l >= 1; --l) {
             const U8 k = ld256_keep(idx + ((size_t)(off + pos) << 3));
-            pos = pos * 8u + count_le<kBin>(k, t);
+            const uint32_t c = count_le<kBin>(k, t);
+            pos = pos * 8u + c;
+            if (kCompact) {              // the key that selected the child = its separator
+                sep = k.v[0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) sep = (c == (uint32_t)i) ? k.v[i] : sep;
+            }
             off += (nb0 + (1u << (3 * l)) - 1u) >> (3 * l);
         }
+    }
+    if (kCompact) {
+        // 32-byte block: v[0..1] = 8 x u8 (sep - cum), v[2..5] = 8 x u16 id low, v[6..7] = 8 x u8 id high.
+        // #(cum_i <= t) = #(sep - cum_i >= sep - t); sep > t, so the threshold is >= 1 and the zero
+        // padding never counts; deltas are <= 255 by construction.
+        const U8 w = ld256_stream(leaf + ((size_t)(m.x + pos) << 3));
+        const uint32_t dt = sep - t;
+        uint32_t c = 0u;
+        if (dt <= 255u) {
+            const uint32_t d4 = dt * 0x01010101u;
+            c = (uint32_t)(__popc(__vcmpgeu4(w.v[0], d4)) + __popc(__vcmpgeu4(w.v[1], d4))) >> 3;
+        }
+        uint32_t lw = w.v[2];
+        lw = (c >> 1) == 1u ? w.v[3] : lw; lw = (c >> 1) == 2u ? w.v[4] : lw; lw = (c >> 1) == 3u ? w.v[5] : lw;
+        const uint32_t hw = (c >> 2) ? w.v[7] : w.v[6];
+        return (int)(((lw >> ((c & 1u) * 16u)) & 0xFFFFu) | (((hw >> ((c & 3u) * 8u)) & 0xFFu) << 16));
     }
     const uint32_t* blk = leaf + ((size_t)(m.x + pos) << 4);
     const U8 keys = ld256_stream(blk);
@@ -162,7 +186,7 @@ __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
     return (int)next;
 }
 
-enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3 };
+enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3, kIndexedCompact = 4 };
 
 // 8 sorted values per lane (descending) -- Batcher odd-even merge sort network, 19 exchanges
 __device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {   // a >= b afterwards
@@ -279,8 +303,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
                     const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
                                                  : uniform53(r.v[0], r.v[1]);
                     int next = -1;
-                    if (kMode == kIndexed) {
-                        next = indexed_step<kBin>(p.meta, p.idx, p.leaf, cur, k53);
+                    if (kMode == kIndexed || kMode == kIndexedCompact) {
+                        next = indexed_step<kBin, kMode == kIndexedCompact>(p.meta, p.idx, p.leaf, cur, k53);
                     } else {
                         const int64_t r0 = __ldg(p.row_ptr + cur);
                         const int64_t r1 = __ldg(p.row_ptr + cur + 1);
@@ -405,7 +429,8 @@ static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_
                              : launch_variant<kFlatF64, false, true, 1>(p, warps, smem, stream);
     const bool bin = v & 2, reg = v & 4;
     const int minb = v >> 4;
-#define PB_V(B_, R_, M_) return launch_variant<kIndexed, B_, R_, M_>(p, warps, smem, stream)
+#define PB_V(B_, R_, M_) return p.leaf_compact ? launch_variant<kIndexedCompact, B_, R_, M_>(p, warps, smem, stream) \
+                                              : launch_variant<kIndexed, B_, R_, M_>(p, warps, smem, stream)
 #define PB_VM(B_, R_) do { if (minb == 5) PB_V(B_, R_, 5); if (minb == 6) PB_V(B_, R_, 6); \
                            if (minb == 7) PB_V(B_, R_, 7); PB_V(B_, R_, 1); } while (0)
     if (bin) { if (reg) PB_VM(true, true); PB_VM(true, false); }
@@ -459,7 +484,7 @@ extern "C" int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_
 }
 
 extern "C" int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* idx,
-                                       const uint32_t* leaf, int64_t num_nodes,
+                                       const uint32_t* leaf, int leaf_format, int64_t num_nodes,
                                        const int32_t* starts, int64_t n, int num_walks,
                                        int walk_length, int num_neighbors, uint64_t seed,
                                        uint32_t epoch, const uint32_t* epoch_dev, int32_t* out_ids,
@@ -474,7 +499,10 @@ extern "C" int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* 
     PB_REQUIRE(meta && leaf && starts && out_ids && out_counts && out_weights && out_nvalid,
                "walk_topt_indexed: null pointer");
     WalkParams p{};
+    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || leaf_format == PB200_LEAF_COMPACT,
+               "walk_topt_indexed: unknown leaf format %d", leaf_format);
     p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
+    p.leaf_compact = leaf_format == PB200_LEAF_COMPACT;
     p.n = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.epoch = epoch;
     p.epoch_dev = epoch_dev;
@@ -490,7 +518,7 @@ extern "C" int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx
                                        uint32_t epoch, int32_t* out_ids, int32_t* out_counts,
                                        float* out_weights, int32_t* out_nvalid, int32_t* trace_out,
                                        pb200_stream_t stream) {
-    return pb200_walk_topt_indexed_ex(meta, idx, leaf, num_nodes, starts, n, num_walks, walk_length,
+    return pb200_walk_topt_indexed_ex(meta, idx, leaf, PB200_LEAF_WIDE, num_nodes, starts, n, num_walks, walk_length,
                                       num_neighbors, seed, epoch, nullptr, out_ids, out_counts,
                                       out_weights, out_nvalid, trace_out, stream);
 }

@@ -28,7 +28,8 @@ class CSR:
     # sampling index (8-ary search tree per row; uint32-quanta graphs only)
     meta: Optional[torch.Tensor] = None     # int32 [N, 4]
     idx: Optional[torch.Tensor] = None      # int32 [idx_blocks, 8]
-    leaf: Optional[torch.Tensor] = None     # int32 [leaf_blocks, 16]
+    leaf: Optional[torch.Tensor] = None     # int32 [leaf_blocks, 16] (wide) or [leaf_blocks, 8] (compact)
+    leaf_format: int = 0                    # N.LEAF_WIDE / N.LEAF_COMPACT
 
     @property
     def device(self):
@@ -62,17 +63,27 @@ def build_walk_index(csr):
     sizes = torch.zeros(2, dtype=torch.int64, device=dev)
     check(lib().pb200_walk_index_sizes(ptr(csr.row_ptr), Nn, ptr(sizes), ptr(ws), ws_bytes, st),
           "walk_index_sizes")
+    rng = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib().pb200_walk_index_leaf_range(ptr(csr.row_ptr), ptr(csr.cum) if csr.num_edges else ptr(csr.row_ptr),
+                                            Nn, ptr(rng), st), "walk_index_leaf_range")
     leaf_blocks, idx_blocks = sizes.tolist()          # build-time sync
+    # compact 32-byte leaves (one 256-bit load per walk step) when ids fit 24 bits and every
+    # 8-edge block spans <= 255 weight quanta; PB200_WALK_LEAF=wide forces the 64-byte format
+    import os
+    compact = (Nn < (1 << 24) and 0 <= int(rng.item()) <= 255 and os.environ.get("PB200_WALK_LEAF", "auto") != "wide")
+    words = 8 if compact else 16
     meta = _aligned_empty(4 * Nn, 16, dev)
     idx = _aligned_empty(8 * max(idx_blocks, 1), 32, dev)
-    leaf = _aligned_empty(16 * max(leaf_blocks, 1), 64, dev)
-    check(lib().pb200_walk_index_build(ptr(csr.row_ptr), ptr(csr.col),
-                                       ptr(csr.cum) if csr.num_edges else ptr(csr.row_ptr), Nn,
-                                       ptr(ws), ptr(meta), ptr(idx), ptr(leaf), st),
+    leaf = _aligned_empty(words * max(leaf_blocks, 1), 64, dev)
+    check(lib().pb200_walk_index_build_ex(ptr(csr.row_ptr), ptr(csr.col),
+                                          ptr(csr.cum) if csr.num_edges else ptr(csr.row_ptr), Nn,
+                                          ptr(ws), ptr(meta), ptr(idx), ptr(leaf), N.LEAF_COMPACT if compact else N.LEAF_WIDE,
+                                          st),
           "walk_index_build")
     csr.meta = meta.view(Nn, 4)
     csr.idx = idx.view(-1, 8)[:idx_blocks]
-    csr.leaf = leaf.view(-1, 16)[:leaf_blocks]
+    csr.leaf = leaf.view(-1, words)[:leaf_blocks]
+    csr.leaf_format = N.LEAF_COMPACT if compact else N.LEAF_WIDE
     return csr
 
 
@@ -148,6 +159,7 @@ def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epo
         raise N.NativeError("walk_topt: a device-side epoch needs the sampling index (use_index=True)")
     if use_index and csr.meta is not None:
         check(lib().pb200_walk_topt_indexed_ex(ptr(csr.meta), ptr(csr.idx), ptr(csr.leaf),
+                                               int(getattr(csr, "leaf_format", N.LEAF_WIDE)),
                                                csr.num_nodes, ptr(s), n, int(num_walks),
                                                int(walk_length), T, int(seed) & (2**64 - 1),
                                                int(epoch) & 0xFFFFFFFF, ptr(epoch_dev), ptr(ids),

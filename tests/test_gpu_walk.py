@@ -133,9 +133,14 @@ def test_sampler_dropin_api(K):
         assert empty_n == [] and empty_w == []
 
 
-def test_walk_index_structure_and_deep_rows(K):
-    """The 8-ary sampling index: block layout vs a numpy restatement, and rows deep enough for
-    3-4 tree levels (degree up to 5000) searched identically to the flat binary search."""
+@pytest.mark.parametrize("leaf_format", ["wide", "compact"])
+def test_walk_index_structure_and_deep_rows(K, leaf_format, monkeypatch):
+    """The 8-ary sampling index: block layout vs a numpy restatement (64-byte leaves, and the
+    compact 32-byte leaves: u8 separator-minus-cum, u16 id low halves, u8 id high bytes), and rows
+    deep enough for 3-4 tree levels (degree up to 5000) searched identically to the flat binary
+    search."""
+    from mre_b200 import _native as NV
+    monkeypatch.setenv("PB200_WALK_LEAF", "wide" if leaf_format == "wide" else "auto")
     rng = np.random.Generator(np.random.PCG64(3))
     degs = [0, 1, 7, 8, 9, 63, 64, 65, 511, 512, 513, 4097, 5000]
     src = np.concatenate([np.full(d, v) for v, d in enumerate(degs)]).astype(np.int64)
@@ -148,6 +153,8 @@ def test_walk_index_structure_and_deep_rows(K):
     csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w[perm]), num_nodes=N)
     row_ptr, col, cum = O.csr_build(ei, w[perm], N, 1)
     meta = _np(csr.meta).view(np.uint32); leaf = _np(csr.leaf).view(np.uint32); idx = _np(csr.idx).view(np.uint32)
+    assert csr.leaf_format == (NV.LEAF_WIDE if leaf_format == "wide" else NV.LEAF_COMPACT)
+    assert leaf.shape[1] == (16 if leaf_format == "wide" else 8)
     lo = io = 0
     for v, d in enumerate(degs):
         a = row_ptr[v]
@@ -155,8 +162,19 @@ def test_walk_index_structure_and_deep_rows(K):
         assert meta[v].tolist() == [lo, d, int(cum[a + d - 1]) if d else 0, io]
         keys = np.full(nb0 * 8, 0xFFFFFFFF, np.uint32); keys[:d] = cum[a:a + d]
         cols = np.full(nb0 * 8, 0xFFFFFFFF, np.uint32); cols[:d] = col[a:a + d].view(np.uint32)
-        np.testing.assert_array_equal(leaf[lo:lo + nb0, :8].reshape(-1), keys)
-        np.testing.assert_array_equal(leaf[lo:lo + nb0, 8:].reshape(-1), cols)
+        if leaf_format == "wide":
+            np.testing.assert_array_equal(leaf[lo:lo + nb0, :8].reshape(-1), keys)
+            np.testing.assert_array_equal(leaf[lo:lo + nb0, 8:].reshape(-1), cols)
+        elif nb0:
+            blk = np.ascontiguousarray(leaf[lo:lo + nb0]).view(np.uint8).reshape(nb0, 32)
+            last = np.minimum(8 * np.arange(nb0) + 7, d - 1)
+            sep = cum[a + last].astype(np.int64)                               # separator of every block
+            want_delta = np.where(keys.reshape(nb0, 8) != 0xFFFFFFFF, sep[:, None] - keys.reshape(nb0, 8).astype(np.int64), 0)
+            assert want_delta.max() <= 255
+            np.testing.assert_array_equal(blk[:, :8], want_delta.astype(np.uint8))
+            ids = np.where(cols.reshape(nb0, 8) != 0xFFFFFFFF, cols.reshape(nb0, 8), 0xFFFFFF).astype(np.uint32)
+            np.testing.assert_array_equal(blk[:, 8:24].copy().view(np.uint16).reshape(nb0, 8), (ids & 0xFFFF).astype(np.uint16))
+            np.testing.assert_array_equal(blk[:, 24:32], (ids >> 16).astype(np.uint8))
         levels, nb = [], nb0
         while nb > 1:
             levels.append(nb); nb = (nb + 7) // 8
@@ -177,3 +195,21 @@ def test_walk_index_structure_and_deep_rows(K):
     for a, b, key in zip(got, flat, ["ids", "counts", "w32", "nvalid", "trace"]):
         np.testing.assert_array_equal(_np(a), _np(b))
         np.testing.assert_array_equal(_np(a), o[key])
+
+
+def test_compact_leaf_falls_back_to_wide_for_heavy_blocks(K):
+    """Blocks spanning more than 255 weight quanta (or >= 2^24 nodes) cannot use the 32-byte leaf:
+    the builder must pick the 64-byte format and the walks must still match the flat search."""
+    from mre_b200 import _native as N
+    rng = np.random.Generator(np.random.PCG64(8))
+    n_edges = 4000
+    src = rng.integers(0, 50, n_edges).astype(np.int64)
+    dst = rng.integers(0, 50, n_edges).astype(np.int64)
+    w = (0.5 * rng.integers(1, 200, n_edges)).astype(np.float32)           # up to 199 quanta per edge
+    ei = np.stack([src, dst])
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=50)
+    assert csr.meta is not None and csr.leaf_format == N.LEAF_WIDE
+    a = K.walk_topt(csr, torch.arange(50), 64, 3, 8, 5, 0, return_trace=True)
+    b = K.walk_topt(csr, torch.arange(50), 64, 3, 8, 5, 0, return_trace=True, use_index=False)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(_np(x), _np(y))
