@@ -335,9 +335,9 @@ def main_b200(args):
                             "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes,
                             "avg_launch_ms": avg_ms, "executed_steps": int(executed.sum()),
                             "share_of_step": sum(walk_ms) / dev_ms,
-                            "limiter": "ncu (profiles/r1_final_ncu_full_walk_dense_pool.txt): LSU data-pipe "
-                                       "wavefronts 66 % of peak (divergent 32 B loads + shared-memory atomics), "
-                                       "issue slots 59 %, DRAM 28 %: the kernel is not HBM-bandwidth bound"}
+                            "limiter": "ncu (profiles/r1_walk_compact_leaf_ncu_details.txt): issue slots 64 % busy, "
+                                       "LSU data-pipe wavefronts 57 % of peak (divergent 32 B loads + shared-memory "
+                                       "atomics), DRAM ~30 %: the kernel is not HBM-bandwidth bound"}
     if ws == 1 and not args.no_cpu_baseline:
         r = run_cpu_port(inp, args.cpu_sample, 3, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
