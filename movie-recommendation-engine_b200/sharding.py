@@ -89,56 +89,75 @@ class PeerBuffers:
         self.shard_rows, self.width, self.count = shard_rows, width, count
         lib = N.lib()
         nbytes = max(shard_rows * width * 4, 16)
-        self._own, handles = [], []
-        for _ in range(count):
-            p = ctypes.c_void_p()
-            N.check(lib.pb200_peer_alloc(nbytes, ctypes.byref(p)), "peer_alloc")
-            h = (ctypes.c_uint8 * 64)()
-            N.check(lib.pb200_peer_export(p, h), "peer_export")
-            self._own.append(p)
-            handles.append(bytes(h))
+        self._own, self._opened, self._arrays, self._keep, self._local = [], [], [], [], []
+        self._flags_local = None
+        self.ok, self.error = True, ""
+        # Every rank runs the same collectives whatever fails locally (no CUDA IPC between these
+        # devices, out of memory, ...): the ranks then agree on ok / not ok, and the caller falls
+        # back to the all-gather exchange on ALL ranks or on none.
+        handles = None
+        try:
+            import os
+            if os.environ.get("PB200_TEST_PEER_FAIL_RANK") == str(self.rank):     # test hook (tools/multi_gpu_check.py)
+                raise RuntimeError("simulated peer-buffer failure")
+            handles = []
+            for b in range(count + 1):                       # `count` row buffers + the barrier flag array
+                p = ctypes.c_void_p()
+                N.check(lib.pb200_peer_alloc(nbytes if b < count else 256, ctypes.byref(p)), "peer_alloc")
+                self._own.append(p)
+                h = (ctypes.c_uint8 * 64)()
+                N.check(lib.pb200_peer_export(p, h), "peer_export")
+                handles.append(bytes(h))
+        except Exception as e:                               # noqa: BLE001 -- reported through self.error
+            self.ok, self.error, handles = False, str(e), None
         gathered = [None] * self.ws
         dist.all_gather_object(gathered, handles, group=group)
-        self._opened, self._arrays, self._keep, self._local = [], [], [], []
-        for b in range(count):
-            ptrs = []
-            for r in range(self.ws):
-                if r == self.rank:
-                    ptrs.append(self._own[b].value)
-                else:
-                    q = ctypes.c_void_p()
-                    hb = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[r][b])
-                    N.check(lib.pb200_peer_open(hb, ctypes.byref(q)), "peer_open")
-                    self._opened.append(q)
-                    ptrs.append(q.value)
-            self._arrays.append((ctypes.c_void_p * self.ws)(*ptrs))
-            raw = _RawCuda(self._own[b].value, (shard_rows, width))
-            self._keep.append(raw)
-            self._local.append(torch.as_tensor(raw, device=dev))
-        # barrier state: one flag array per rank in peer memory + this rank's sequence counter
-        fp = ctypes.c_void_p()
-        N.check(lib.pb200_peer_alloc(256, ctypes.byref(fp)), "peer_alloc")
-        self._own.append(fp)
-        self._flags_local = torch.as_tensor(_RawCuda(fp.value, (64,)), device=dev)
-        self._flags_local.zero_()
-        fh = (ctypes.c_uint8 * 64)()
-        N.check(lib.pb200_peer_export(fp, fh), "peer_export")
-        fgath = [None] * self.ws
-        dist.all_gather_object(fgath, bytes(fh), group=group)
-        fptrs = []
-        for r in range(self.ws):
-            if r == self.rank:
-                fptrs.append(fp.value)
-            else:
-                q = ctypes.c_void_p()
-                N.check(lib.pb200_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(fgath[r]), ctypes.byref(q)),
-                        "peer_open")
-                self._opened.append(q)
-                fptrs.append(q.value)
-        self._flag_ptrs = torch.tensor(fptrs, dtype=torch.int64, device=dev)
-        self._seq = torch.zeros(2, dtype=torch.int32, device=dev)      # [sequence counter, error flag]
+        if self.ok and any(g is None for g in gathered):
+            self.ok, self.error = False, "a peer could not allocate / export its buffers"
+        if self.ok:
+            try:
+                table = []                                   # table[b][r]: buffer b of rank r, mapped here
+                for b in range(count + 1):
+                    ptrs = []
+                    for r in range(self.ws):
+                        if r == self.rank:
+                            ptrs.append(self._own[b].value)
+                        else:
+                            q = ctypes.c_void_p()
+                            hb = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[r][b])
+                            N.check(lib.pb200_peer_open(hb, ctypes.byref(q)), "peer_open")
+                            self._opened.append(q)
+                            ptrs.append(q.value)
+                    table.append(ptrs)
+                for b in range(count):
+                    self._arrays.append((ctypes.c_void_p * self.ws)(*table[b]))
+                    raw = _RawCuda(self._own[b].value, (shard_rows, width))
+                    self._keep.append(raw)
+                    self._local.append(torch.as_tensor(raw, device=dev))
+                # barrier state: one flag array per rank in peer memory + this rank's sequence counter
+                flags_raw = _RawCuda(self._own[count].value, (64,))
+                self._keep.append(flags_raw)
+                self._flags_local = torch.as_tensor(flags_raw, device=dev)
+                self._flags_local.zero_()
+                self._flag_ptrs = torch.tensor(table[count], dtype=torch.int64, device=dev)
+                self._seq = torch.zeros(2, dtype=torch.int32, device=dev)      # [sequence counter, error flag]
+            except Exception as e:                           # noqa: BLE001
+                self.ok, self.error = False, str(e)
         torch.cuda.synchronize(dev)
-        dist.barrier(group=group)                                     # every rank's flags are zeroed and mapped
+        agree = torch.tensor([1 if self.ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)   # also: every rank's flags are zeroed and mapped
+        if int(agree.item()) == 0:
+            if self.ok:
+                self.ok, self.error = False, "a peer could not map the exchange buffers"
+            self._release()
+
+    def _release(self):
+        from . import _native as N
+        for q in self._opened:
+            N.lib().pb200_peer_close(q)
+        for p in self._own:
+            N.lib().pb200_peer_free(p)
+        self._opened, self._own, self._local, self._keep, self._flags_local, self._arrays = [], [], [], [], None, []
 
     def ptr_array(self, b):
         return self._arrays[b]
@@ -158,29 +177,33 @@ class PeerBuffers:
         return bool(self._seq[1].item())
 
     def close(self):
-        from . import _native as N
         torch.cuda.synchronize(self.dev)
         dist.barrier(group=self.group)
-        for q in self._opened:
-            N.lib().pb200_peer_close(q)
-        for p in self._own:
-            N.lib().pb200_peer_free(p)
-        self._opened, self._own, self._local, self._keep, self._flags_local = [], [], [], [], None
+        self._release()
 
 
 _PEER_CACHE = {}
 
 
 def peer_buffers(count, shard_rows, width, dev, group=None):
+    """The cached PeerBuffers for this shape, or None when the ranks agreed that peer memory is not
+    usable here (the caller then all-gathers; the decision is collective, so all ranks take the
+    same path)."""
     key = (count, shard_rows, width, str(dev), id(group))
     if key not in _PEER_CACHE:
-        _PEER_CACHE[key] = PeerBuffers(count, shard_rows, width, dev, group)
-    return _PEER_CACHE[key]
+        pb = PeerBuffers(count, shard_rows, width, dev, group)
+        if not pb.ok and pb.rank == 0:
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({pb.error}); falling back to all-gather of h")
+        _PEER_CACHE[key] = pb
+    pb = _PEER_CACHE[key]
+    return pb if pb.ok else None
 
 
 def release_peer_buffers():
     for pb in _PEER_CACHE.values():
-        pb.close()
+        if pb.ok:
+            pb.close()
     _PEER_CACHE.clear()
 
 
@@ -217,10 +240,12 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward
     PRE = 0 if model.precision == N.PREC_FP32 else N.IN_A1_TF32
     h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
+    pb = None
     if _use_peer_exchange(model, dev, ws):
-        # neighbour rows are read from their owners' memory; no all-gather
         srows = shard_size(num_items, ws)
         pb = peer_buffers(model.num_layers, srows, h_loc.size(1), dev, group)
+    if pb is not None:
+        # neighbour rows are read from their owners' memory; no all-gather
         for i in range(model.num_layers):
             mine = pb.local(i)[:hi - lo]
             mine.copy_(h_loc)

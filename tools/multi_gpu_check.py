@@ -35,6 +35,18 @@ for k in range(3):
     sampler.epoch = 100 + 2 * k
     want = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
     assert torch.equal(got, want), f"rank {rank}: graph replay {k} differs from the eager step"
+# a rank that cannot set up peer memory: ALL ranks must fall back to the all-gather exchange
+os.environ["PB200_TEST_PEER_FAIL_RANK"] = "1"
+SH._PEER_CACHE.clear()                       # (leaks the earlier buffers: test only)
+import warnings
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    sampler.epoch = 0
+    mine_fb = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
+assert all(not pb.ok for pb in SH._PEER_CACHE.values()), f"rank {rank}: fallback was not collective"
+assert torch.equal(mine_fb, full[lo:hi]), f"rank {rank}: all-gather fallback differs"
+del os.environ["PB200_TEST_PEER_FAIL_RANK"]
+SH._PEER_CACHE.clear()
 emb = full
 # item-sharded exact search + merge == unsharded
 q = emb[:257].contiguous()
