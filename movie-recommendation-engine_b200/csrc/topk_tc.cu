@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
         unsigned long long* wl = lists + (size_t)row0 * ks;  // row r of the warp: wl[r * ks + rank]
         int tc_ = 0;
         long long sp_wait = 0, sp_ld = 0, sp_fast = 0, sp_slow = 0, sp_groups = 0, sp_slowg = 0, sp_t0 = SP_NOW();
+        long long sp_late_slow = 0, sp_late_slowg = 0, sp_late_cand = 0, sp_late_votes = 0, sp_cand = 0;
         for (int64_t t = t_begin; t < t_end;) {
             const Seg sg = segment(t);
             t = sg.t_next;
@@ -340,6 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 m8[i] = __ballot_sync(kFull, f[i] >= thr_t && col0 + g * 8 + i < n_end);
+#ifdef PB200_SEARCH_PROFILE
+                            {
+                                int nc = 0;
+                                for (int i = 0; i < 8; ++i) nc += __popc(m8[i]);
+                                sp_cand += nc;
+                                if (nt >= 40) { sp_late_cand += nc; sp_late_slowg += 1; SP_ADD(sp_late_votes, s0); }
+                            }
+#endif
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 if (m8[i]) {
@@ -349,14 +358,19 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
                                 }
                             }
                             SP_ADD(sp_slow, s0);
+#ifdef PB200_SEARCH_PROFILE
+                            if (nt >= 40) SP_ADD(sp_late_slow, s0);
+#endif
                         }
                     }
                 }
             }
 #ifdef PB200_SEARCH_PROFILE
             if (t >= t_end && lane == 0 && blockIdx.x == 3)
-                printf("scan warp %d: total %lld  wait_tfull %lld  tmem_ld %lld  fast %lld  slow %lld  groups %lld  slow_groups %lld\n",
-                       e, (long long)(clock64() - sp_t0), sp_wait, sp_ld, sp_fast, sp_slow, sp_groups, sp_slowg);
+                printf("scan warp %d: total %lld  wait_tfull %lld  tmem_ld %lld  fast %lld  slow %lld  groups %lld  slow_groups %lld  "
+                       "candidates %lld | tiles >= 40 of a segment: slow %lld  slow_groups %lld  candidates %lld  votes %lld\n",
+                       e, (long long)(clock64() - sp_t0), sp_wait, sp_ld, sp_fast, sp_slow, sp_groups, sp_slowg, sp_cand,
+                       sp_late_slow, sp_late_slowg, sp_late_cand, sp_late_votes);
 #endif
             // segment done: every row's sorted list -> short_keys[sp][q][0..ks)
             __syncwarp();
