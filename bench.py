@@ -246,7 +246,15 @@ def main_b200(args):
     barrier()
     if ws > 1 and not args.no_graph:
         from mre_b200.graphs import GraphedEmbeddings
-        graphed = GraphedEmbeddings(model, x_dev, sampler, T, num_items=M)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            graphed = GraphedEmbeddings(model, x_dev, sampler, T, num_items=M)
+        except Exception as e:          # noqa: BLE001 -- capture unsupported here: keep the eager step
+            print(f"[bench] rank {rank}: CUDA-graph capture failed ({e}); eager launches", file=sys.stderr)
+            graphed, ok[0] = None, 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks replay, or none
+        if int(ok.item()) == 0:
+            graphed = None
         for _ in range(3):
             step_device()
         barrier()
