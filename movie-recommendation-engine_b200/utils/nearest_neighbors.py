@@ -164,9 +164,15 @@ class WeakANDIndex:
         lay = getattr(self, "_tc_layout", None)
         if (self.precision != "fp32" and lay is not None and q.size(0) >= K.TOPK_TC_MIN_QUERIES
                 and K.ivf_search_tc_supported(q.size(0), lay[0].size(0), self.dim, k, self.num_partitions)):
-            dist, ids = K.ivf_search_tc(q, probes, *self._lists, lay, self.num_partitions, k)
-        else:
-            dist, ids = K.ivf_search(q, probes, *self._lists, k)
+            st = {}
+            dist, ids = K.ivf_search_tc(q, probes, *self._lists, lay, self.num_partitions, k, stats=st)
+            out = _np_results(dist, ids)                       # (synchronises: the counter below is ready)
+            # near-tied data (e.g. collapsed embeddings) defeats the TF32 certificate and
+            # every query is re-run by the list-scan kernel anyway: stop paying for the tensor-core pass
+            if self.precision == "auto" and int(st["list_scan_reruns"].item()) > q.size(0) // 4:
+                self.precision = "fp32"
+            return out
+        dist, ids = K.ivf_search(q, probes, *self._lists, k)
         return _np_results(dist, ids)
 
 
@@ -178,6 +184,7 @@ class FlatL2Index:
         self.device = N.device_of(device=device)
         self._x = torch.empty((0, dim), dtype=torch.float32, device=self.device)
         self.ntotal = 0
+        self.precision = "auto"      # "auto" | "fp32" | "tf32" (kernels.topk); see search()
 
     def add(self, embeddings):
         self._x = torch.cat([self._x, _to_f32_tensor(embeddings).to(self.device)]).contiguous()
@@ -185,7 +192,14 @@ class FlatL2Index:
 
     def search(self, queries, k):
         q = _to_f32_tensor(queries).to(self.device).contiguous()
-        return _np_results(*K.topk(q, self._x, k, N.METRIC_L2))
+        st = {}
+        out = _np_results(*K.topk(q, self._x, k, N.METRIC_L2, precision=self.precision, stats=st))
+        # results are the fp32 kernel's either way; if the certificate sends most queries back to it
+        # (near-tied data), skip the tensor-core pass from now on
+        if (self.precision == "auto" and st.get("path") == "tf32"
+                and int(st["fp32_reruns"].item()) > q.size(0) // 4):
+            self.precision = "fp32"
+        return out
 
 
 def benchmark_search_methods(embeddings, queries, k=10, methods=None):

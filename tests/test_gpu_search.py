@@ -343,3 +343,23 @@ def test_rank_of_target_ties_edges_and_size(K):
     assert bool((r_in <= 10).all())
     in_top = (ids.cpu() == far[:, None].to(torch.int32)).any(1)
     assert bool(((r_far <= 10) == in_top).all())
+
+
+def test_indexes_leave_the_tensor_core_path_on_near_tied_data(K):
+    """Collapsed embeddings fail the TF32 certificate for most queries: results
+    stay exact (fp32 re-runs) and the index classes switch themselves to the fp32 kernels."""
+    from mre_b200.utils.nearest_neighbors import FlatL2Index, WeakANDIndex
+    rng = np.random.Generator(np.random.PCG64(17))
+    base = rng.standard_normal((1, 64)).astype(np.float32)
+    x = base + 0.004 * rng.standard_normal((5000, 64)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    flat = FlatL2Index(64); flat.add(x)
+    d1, i1 = flat.search(x[:600], 10)
+    assert flat.precision == "fp32"
+    d2, i2 = flat.search(x[:600], 10)                     # now the CUDA-core path: same answer
+    np.testing.assert_array_equal(i1, i2); np.testing.assert_array_equal(d1, d2)
+    ivf = WeakANDIndex(64, 16, 10)
+    ivf.build(x)
+    a1 = ivf.search(x[:600], 10)
+    a2 = ivf.search(x[:600], 10)
+    np.testing.assert_array_equal(a1[1], a2[1]); np.testing.assert_array_equal(a1[0], a2[0])
