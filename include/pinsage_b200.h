@@ -112,6 +112,24 @@ int pb200_walk_index_build(const int64_t* row_ptr, const int32_t* col, const voi
  * leaf block instead of 64).  The selected edges are identical. */
 #define PB200_LEAF_WIDE 0
 #define PB200_LEAF_COMPACT 1
+/* BUCKET: direct-addressed index (csrc/walk_bucket.cu) -- meta uint32 [4*N] {first bucket, degree,
+ * row total S, shift s}; bucket j of a row is one 32-byte block with every edge overlapping
+ * [j 2^s, (j+1) 2^s) of the row's weight axis {8 x u8 min(cum - j 2^s, 2^s), 8 x id byte 0, 8 x id
+ * byte 1, 8 x id byte 2}.  A walk step is meta -> bucket (t >> s): two dependent loads.  Needs every
+ * weight >= 1 quantum and num_nodes <= 2^24; idx is unused (may be NULL).  Same selected edges. */
+#define PB200_LEAF_BUCKET 2
+/*   1. pb200_walk_bucket_plan: per-row shift + bucket counts -> meta {_, degree, S, s}; info_out
+ *      uint64 [2] (device) = {total buckets, number of zero-weight edges (format unusable if != 0)};
+ *      row offsets stay in `workspace` for step 3;
+ *   2. the caller allocates leaf (32 bytes per bucket, 32 B aligned);
+ *   3. pb200_walk_bucket_fill writes the buckets and meta[.].x. */
+size_t pb200_walk_bucket_workspace_bytes(int64_t num_nodes);
+int pb200_walk_bucket_plan(const int64_t* row_ptr, const void* cum, int64_t num_nodes, uint32_t* meta,
+                           uint64_t* info_out, void* workspace, size_t workspace_bytes,
+                           pb200_stream_t stream);
+int pb200_walk_bucket_fill(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                           int64_t num_nodes, const void* workspace, uint32_t* meta, uint32_t* leaf,
+                           uint64_t total_buckets, pb200_stream_t stream);
 /* max over all 8-edge leaf blocks of (last - first cumulative weight) -> *max_range_out (device u32) */
 int pb200_walk_index_leaf_range(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
                                 uint32_t* max_range_out, pb200_stream_t stream);

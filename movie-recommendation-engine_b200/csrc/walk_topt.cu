@@ -33,6 +33,7 @@ struct WalkParams {
     const uint32_t* __restrict__ idx;
     const uint32_t* __restrict__ leaf;
     int leaf_compact;                       // PB200_LEAF_COMPACT: 32-byte leaf blocks
+    int leaf_format;
     int64_t n;
     int64_t num_nodes;
     int W, L, T;
@@ -186,7 +187,34 @@ __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
     return (int)next;
 }
 
-enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3, kIndexedCompact = 4 };
+
+// ---- bucket step (walk_bucket.cu): meta -> ONE 32-byte bucket, two dependent loads ----
+// (a, b) are the two Philox words of this step: k53 = (a >> 5) * 2^26 + (b >> 6) (uniform53),
+// t = floor(k53 * S / 2^53) = (kh * S + mulhi(kl, S)) >> 21 with kh = k53 >> 32, kl = low word
+// (floor(floor(x / 2^32) / 2^21) = floor(x / 2^53); kh * S * 2^32 is a multiple of 2^32).
+__device__ __forceinline__ int bucket_step(const uint4* __restrict__ meta,
+                                           const uint32_t* __restrict__ leaf, int cur, uint32_t a,
+                                           uint32_t b) {
+    const uint4 m = __ldg(meta + cur);   // {first bucket, degree, row total S, shift s}
+    if (m.y == 0u) return -1;
+    const uint32_t kh = a >> 11;
+    const uint32_t kl = ((a >> 5) << 26) | (b >> 6);
+    const uint64_t prod = (uint64_t)kh * m.z + (uint64_t)__umulhi(kl, m.z);
+    const uint32_t t = (uint32_t)(prod >> 21);
+    const uint32_t j = t >> m.w;
+    const uint32_t tr = t - (j << m.w);
+    const U8 w = ld256_stream(leaf + ((size_t)(m.x + j) << 3));
+    // slots with rel <= tr, bytewise: 0x80 + tr - rel keeps bit 7 iff rel <= tr (rel <= 128, tr <= 127:
+    // no borrow crosses a byte).  rel is ascending and the edge holding t is in the bucket: c <= 7.
+    const uint32_t t4 = tr * 0x01010101u + 0x80808080u;
+    const uint32_t c = (uint32_t)(__popc((t4 - w.v[0]) & 0x80808080u) + __popc((t4 - w.v[1]) & 0x80808080u));
+    const uint32_t r0 = __byte_perm(w.v[2], w.v[3], c);
+    const uint32_t r1 = __byte_perm(w.v[4], w.v[5], c);
+    const uint32_t r2 = __byte_perm(w.v[6], w.v[7], c);
+    return (int)(__byte_perm(__byte_perm(r0, r1, 0x0040u), r2, 0x0410u) & 0x00FFFFFFu);
+}
+
+enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3, kIndexedCompact = 4, kIndexedBucket = 5 };
 
 // 8 sorted values per lane (descending) -- Batcher odd-even merge sort network, 19 exchanges
 __device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {   // a >= b afterwards
@@ -303,7 +331,10 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
                     const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
                                                  : uniform53(r.v[0], r.v[1]);
                     int next = -1;
-                    if (kMode == kIndexed || kMode == kIndexedCompact) {
+                    if (kMode == kIndexedBucket) {
+                        next = (l & 1) ? bucket_step(p.meta, p.leaf, cur, r.v[2], r.v[3])
+                                       : bucket_step(p.meta, p.leaf, cur, r.v[0], r.v[1]);
+                    } else if (kMode == kIndexed || kMode == kIndexedCompact) {
                         next = indexed_step<kBin, kMode == kIndexedCompact>(p.meta, p.idx, p.leaf, cur, k53);
                     } else {
                         const int64_t r0 = __ldg(p.row_ptr + cur);
@@ -376,6 +407,162 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
     }
 }
 
+
+// ---- lean kernel for the bucket index (the default path) --------------------------------
+// Same algorithm as walk_topt_kernel, rebuilt around what ncu showed on the tree-index version
+// (profiles/r1_walk_compact_leaf_ncu_details.txt: issue slots 64 %, 18 of 32 lanes active, 3560 warp
+// instructions per start node): (i) bucket_step -- two dependent loads and ~35 instructions per step
+// instead of 3-5 loads and ~160; (ii) warp-uniform control flow: every lane runs every round and
+// every probe iteration under a predicate, so the warp never splits (the old kernel ran its top-T
+// sort twice -- once for the 4 lanes of the last round, once for the other 28 -- and its hash
+// atomics once per distinct probe-loop exit); (iii) Philox round keys precomputed on the host;
+// (iv) double hashing instead of linear probing; (v) weights by IEEE fp32 division, which equals
+// (float)((double)c / total) for c <= total <= 255 (tests/test_walk_host_logic.py checks all pairs).
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+
+__device__ __forceinline__ Philox4 philox_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKeys& k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.k1[r];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    }
+    Philox4 o;
+    o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+    return o;
+}
+
+// All 32 lanes call; lanes with !alive only take part in the votes.  256 slots.
+__device__ __forceinline__ void table_insert_uniform(int32_t* keys, int node, bool alive, uint32_t fs) {
+    const uint32_t hh = (uint32_t)node * 2654435761u;
+    uint32_t h = hh >> 24;
+    const uint32_t step = ((hh >> 8) & 0xFEu) | 1u;      // odd: visits every slot of the 2^8 table
+    bool pending = alive;
+    while (__any_sync(kFull, pending)) {
+        if (pending) {
+            const int prev = atomicCAS(&keys[h], kEmpty, node);
+            if (prev == kEmpty || prev == node) pending = false;
+            else h = (h + step) & 255u;
+        }
+    }
+    if (alive) {
+        atomicAdd(reinterpret_cast<uint32_t*>(keys) + 256 + h, 1u);
+        atomicMin(reinterpret_cast<uint32_t*>(keys) + 512 + h, fs);
+    }
+}
+
+// Register top-T for the 256-slot table (see select_topt_regs); fp32 division for the weights.
+__device__ __forceinline__ void select_topt_fast(const WalkParams& p, const int32_t* keys, int64_t s, int lane) {
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(keys) + 256;
+    const uint32_t* first = cnt + 256;
+    uint32_t k[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int slot = i * 32 + lane;
+        const uint32_t c = cnt[slot];
+        k[i] = c ? ((c << 17) | ((255u - first[slot]) << 9) | (uint32_t)slot) : 0u;
+    }
+    sort8_desc(k);
+    int my_id = -1; uint32_t my_cnt = 0, total = 0;
+    int nvalid = 0;
+    for (int j = 0; j < p.T; ++j) {
+        const uint32_t m = __reduce_max_sync(kFull, k[0]);
+        if (m == 0) break;                     // warp-uniform: fewer than T distinct nodes
+        const bool win = k[0] == m;            // keys are unique (slot bits)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) k[i] = win ? k[i + 1] : k[i];
+        k[7] = win ? 0u : k[7];
+        const uint32_t c = m >> 17;
+        const int node = keys[m & 255u];       // broadcast
+        total += c;
+        my_id = lane == j ? node : my_id;
+        my_cnt = lane == j ? c : my_cnt;
+        ++nvalid;
+    }
+    if (lane < p.T) {
+        const bool has = lane < nvalid;
+        const int64_t o = s * p.T + lane;
+        p.out_ids[o] = has ? my_id : -1;
+        p.out_counts[o] = has ? (int32_t)my_cnt : 0;
+        p.out_w[o] = has ? __fdiv_rn((float)my_cnt, (float)total) : 0.0f;
+    }
+    if (lane == 0) p.out_nvalid[s] = nvalid;
+}
+
+template <int kL, bool kTrace, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const WalkParams p, const PhiloxKeys pk) {
+    extern __shared__ int32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int32_t* keys = smem + warp * 768;                  // [keys | cnt | first] x 256 slots
+    const int L = kL ? kL : p.L;
+    const uint32_t epoch = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
+    for (int64_t s = (int64_t)blockIdx.x * 8 + warp; s < p.n; s += (int64_t)gridDim.x * 8) {
+        {   // clear: lane owns 8 consecutive slots of each array (two 128-bit stores each)
+            int4* k4 = reinterpret_cast<int4*>(keys) + lane * 2;
+            const int4 e = make_int4(-1, -1, -1, -1), z = make_int4(0, 0, 0, 0);
+            k4[0] = e; k4[1] = e; k4[64] = z; k4[65] = z; k4[128] = e; k4[129] = e;
+        }
+        __syncwarp();
+        const int start = __ldg(p.starts + s);
+        for (int base = 0; base < p.W; base += 32) {
+            const int walk = base + lane;
+            bool alive = walk < p.W;
+            int cur = start;
+            Philox4 r;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                if ((l & 1) == 0)
+                    r = philox_keys((uint32_t)start, (uint32_t)walk, (uint32_t)(l >> 1), epoch, pk);
+                const uint32_t a = (l & 1) ? r.v[2] : r.v[0], b = (l & 1) ? r.v[3] : r.v[1];
+                int next = -1;
+                if (alive) next = bucket_step(p.meta, p.leaf, cur, a, b);
+                if (kTrace) { if (walk < p.W) p.trace_out[(s * p.W + walk) * L + l] = next; }
+                alive = next >= 0;             // dead end: random_walk.py:68-69
+                table_insert_uniform(keys, next, alive, (uint32_t)(walk * L + l));
+                cur = alive ? next : cur;
+            }
+        }
+        __syncwarp();
+        select_topt_fast(p, keys, s, lane);
+        __syncwarp();
+    }
+}
+
+static void philox_round_keys(uint32_t seed_lo, uint32_t seed_hi, PhiloxKeys& k) {
+    uint32_t k0 = seed_lo, k1 = seed_hi;
+    for (int r = 0; r < 10; ++r) { k.k0[r] = k0; k.k1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
+template <int kL, bool kTrace, int kMinBlocks>
+static int launch_bucket_variant(const WalkParams& p, const PhiloxKeys& pk, cudaStream_t stream) {
+    int64_t blocks = ceil_div(p.n, (int64_t)8);
+    const int64_t cap = (int64_t)kSMs * 32;
+    if (blocks > cap) blocks = cap;
+    walk_bucket_kernel<kL, kTrace, kMinBlocks><<<(unsigned)blocks, 256, 8 * 768 * sizeof(int32_t), stream>>>(p, pk);
+    return check_launch("walk_bucket_kernel");
+}
+
+// W*L <= 200 visits in a 256-slot table (load <= 0.78), first-visit index < 255, T <= 32
+static bool bucket_fast_ok(const WalkParams& p) { return p.W * p.L <= 200 && p.T <= 32; }
+
+static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
+    static const int minb = [] { const char* e = getenv("PB200_WALK_MINBLOCKS"); return e ? atoi(e) : 6; }();
+    PhiloxKeys pk;
+    philox_round_keys(p.seed_lo, p.seed_hi, pk);
+#define PB_B(L_, T_) do { if (minb == 8) return launch_bucket_variant<L_, T_, 8>(p, pk, stream); \
+                          if (minb == 7) return launch_bucket_variant<L_, T_, 7>(p, pk, stream); \
+                          if (minb == 5) return launch_bucket_variant<L_, T_, 5>(p, pk, stream); \
+                          return launch_bucket_variant<L_, T_, 6>(p, pk, stream); } while (0)
+    if (p.trace_out) { if (p.L == 2) PB_B(2, true); PB_B(0, true); }
+    if (p.L == 2) PB_B(2, false);
+    PB_B(0, false);
+#undef PB_B
+}
+
 // Measured and rejected (B200, config C2, tools/tune_walk.py; baseline 0.360 ms per launch):
 //   * 2 or 4 walks per lane with the loads of every stage (meta / index level / leaf) issued
 //     back to back: 0.361-0.524 ms.  More requests in flight do not help: ncu shows the LSU
@@ -429,6 +616,10 @@ static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_
     if (!p.meta)
         return cum_kind == 0 ? launch_variant<kFlatU32, false, true, 1>(p, warps, smem, stream)
                              : launch_variant<kFlatF64, false, true, 1>(p, warps, smem, stream);
+    if (p.leaf_format == PB200_LEAF_BUCKET) {
+        if (bucket_fast_ok(p) && !(v & 1)) return launch_walk_bucket(p, stream);
+        return launch_variant<kIndexedBucket, false, true, 1>(p, warps, smem, stream);   // generic sizes
+    }
     const bool bin = v & 2, reg = v & 4;
     const int minb = v >> 4;
 #define PB_V(B_, R_, M_) return p.leaf_compact ? launch_variant<kIndexedCompact, B_, R_, M_>(p, warps, smem, stream) \
@@ -501,8 +692,9 @@ extern "C" int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* 
     PB_REQUIRE(meta && leaf && starts && out_ids && out_counts && out_weights && out_nvalid,
                "walk_topt_indexed: null pointer");
     WalkParams p{};
-    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || leaf_format == PB200_LEAF_COMPACT,
+    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || leaf_format == PB200_LEAF_COMPACT || leaf_format == PB200_LEAF_BUCKET,
                "walk_topt_indexed: unknown leaf format %d", leaf_format);
+    p.leaf_format = leaf_format;
     p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
     p.leaf_compact = leaf_format == PB200_LEAF_COMPACT;
     p.n = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;

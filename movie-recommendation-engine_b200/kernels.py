@@ -51,10 +51,47 @@ def _aligned_empty(n_int32, align, dev):
     return t
 
 
-def build_walk_index(csr):
-    """Adds the 8-ary sampling index to a uint32-quanta CSR (pb200_walk_index_*)."""
+def _build_bucket_index(csr):
+    """Direct-addressed bucket index (pb200_walk_bucket_*): meta -> one 32-byte bucket per walk step.
+    Returns False (csr untouched) when the format does not apply: a zero-weight edge, more than
+    2^24 nodes, or weights so heavy that the buckets would take more than ~48 bytes per edge."""
+    dev = csr.device
+    st = stream_ptr(dev)
+    Nn, E = csr.num_nodes, csr.num_edges
+    if Nn > (1 << 24) or E == 0:
+        return False
+    ws_bytes = lib().pb200_walk_bucket_workspace_bytes(Nn)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    meta = _aligned_empty(4 * Nn, 16, dev)
+    info = torch.zeros(2, dtype=torch.int64, device=dev)
+    check(lib().pb200_walk_bucket_plan(ptr(csr.row_ptr), ptr(csr.cum), Nn, ptr(meta), ptr(info), ptr(ws),
+                                       ws_bytes, st), "walk_bucket_plan")
+    buckets, zero_edges = info.tolist()               # build-time sync
+    if zero_edges or buckets >= (1 << 32) or buckets * 32 > 48 * E + 64 * Nn:
+        return False
+    leaf = _aligned_empty(8 * max(buckets, 1), 32, dev)
+    check(lib().pb200_walk_bucket_fill(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cum), Nn, ptr(ws), ptr(meta),
+                                       ptr(leaf), buckets, st), "walk_bucket_fill")
+    csr.meta = meta.view(Nn, 4)
+    csr.idx = None
+    csr.leaf = leaf.view(-1, 8)[:buckets]
+    csr.leaf_format = N.LEAF_BUCKET
+    return True
+
+
+def build_walk_index(csr, leaf=None):
+    """Adds a sampling index to a uint32-quanta CSR.  `leaf` (or PB200_WALK_LEAF): "auto" (bucket index
+    when it applies, else the 8-ary tree with compact or wide leaves), "bucket", "compact", "wide"."""
     if csr.cum_kind != 0 or csr.num_nodes == 0:
         return csr
+    import os
+    want = (leaf or os.environ.get("PB200_WALK_LEAF", "auto")).lower()
+    if want in ("auto", "bucket"):
+        if _build_bucket_index(csr):
+            return csr
+        if want == "bucket":
+            raise N.NativeError("the bucket sampling index does not apply to this graph (zero-weight edges, "
+                                "more than 2^24 nodes, or very heavy weights)")
     dev = csr.device
     st = stream_ptr(dev)
     Nn = csr.num_nodes
@@ -69,8 +106,7 @@ def build_walk_index(csr):
     leaf_blocks, idx_blocks = sizes.tolist()          # build-time sync
     # compact 32-byte leaves (one 256-bit load per walk step) when ids fit 24 bits and every
     # 8-edge block spans <= 255 weight quanta; PB200_WALK_LEAF=wide forces the 64-byte format
-    import os
-    compact = (Nn < (1 << 24) and 0 <= int(rng.item()) <= 255 and os.environ.get("PB200_WALK_LEAF", "auto") != "wide")
+    compact = (Nn < (1 << 24) and 0 <= int(rng.item()) <= 255 and want != "wide")
     words = 8 if compact else 16
     meta = _aligned_empty(4 * Nn, 16, dev)
     idx = _aligned_empty(8 * max(idx_blocks, 1), 32, dev)
@@ -89,6 +125,7 @@ def build_walk_index(csr):
 
 def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_float=False,
               index=True):
+    """index: True / "auto" / "bucket" / "compact" / "wide" (see build_walk_index), False = CSR only."""
     dev = N.device_of(edge_index, edge_weights, device=device)
     ei = N.dev_tensor(edge_index, torch.int64, dev)
     if ei.dim() != 2 or ei.size(0) != 2:
@@ -135,7 +172,7 @@ def csr_build(edge_index, edge_weights=None, num_nodes=None, device=None, force_
                              "(the reference's np.random.choice would raise on NaN probabilities)")
         break
     csr = CSR(row_ptr, col, cum, 0 if quant_shift >= 0 else 1, quant_shift, num_nodes, E)
-    return build_walk_index(csr) if index else csr
+    return build_walk_index(csr, leaf=index if isinstance(index, str) else None) if index else csr
 
 
 def u32_add(counter, delta):

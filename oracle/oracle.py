@@ -126,6 +126,59 @@ def _pick(cum, r0, r1, k53):
     return r0 + min(i, r1 - r0 - 1)
 
 
+def walk_bucket_index(row_ptr, col, cum):
+    """numpy restatement of the direct-addressed sampling index the walk kernel reads
+    (csrc/walk_bucket.cu, PB200_LEAF_BUCKET): per row a shift s and ceil(S / 2^s) 32-byte buckets
+    {8 x u8 min(cum - j 2^s, 2^s) (unused: 128), 8 x id byte 0, 8 x id byte 1, 8 x id byte 2}.
+    Returns (meta uint32 [N, 4] = {first bucket, degree, S, s}, leaf uint8 [buckets, 32]) or None
+    when a zero-weight edge makes the format unusable.  Pure loops: small graphs only."""
+    N = len(row_ptr) - 1
+    meta = np.zeros((N, 4), np.uint32)
+    blocks = []
+    for v in range(N):
+        a, b = int(row_ptr[v]), int(row_ptr[v + 1])
+        c = cum[a:b].astype(np.int64)
+        deg = b - a
+        S = int(c[-1]) if deg else 0
+        prev = np.concatenate([[0], c[:-1]]) if deg else c
+        if deg and np.any(c == prev):
+            return None
+        s = 7
+        for i in range(deg - 8):                       # edges i..i+8 must not share a bucket
+            x = int(c[i] - 1) ^ int(c[i + 7])
+            s = min(s, x.bit_length() - 1)
+        meta[v] = (len(blocks), deg, S, s)
+        w = 1 << s
+        for j in range(((S - 1) >> s) + 1 if S else 0):
+            lo = j << s
+            blk = np.zeros(32, np.uint8); blk[:8] = 128
+            first = int(np.searchsorted(c, lo, side="right"))      # first edge with cum > lo
+            q = 0
+            e = first
+            while e < deg and (e == first or prev[e] < lo + w):
+                assert q < 8, "bucket overflow: the shift rule is wrong"
+                blk[q] = min(int(c[e]) - lo, w)
+                nid = int(col[a + e])
+                blk[8 + q], blk[16 + q], blk[24 + q] = nid & 255, (nid >> 8) & 255, (nid >> 16) & 255
+                q += 1; e += 1
+            blocks.append(blk)
+    leaf = np.stack(blocks) if blocks else np.zeros((0, 32), np.uint8)
+    return meta, leaf
+
+
+def walk_bucket_pick(meta, leaf, v, k53):
+    """The bucket walk step: neighbour chosen at node v for the 53-bit uniform numerator k53, or -1."""
+    first, deg, S, s = (int(x) for x in meta[v])
+    if deg == 0:
+        return -1
+    t = (k53 * S) >> 53
+    blk = leaf[first + (t >> s)]
+    tr = t & ((1 << s) - 1)
+    c = int(np.sum(blk[:8] <= tr))
+    assert c < 8
+    return int(blk[8 + c]) | (int(blk[16 + c]) << 8) | (int(blk[24 + c]) << 16)
+
+
 def walk_topt(row_ptr, col, cum, starts, W, L, T, seed, epoch=0, return_trace=False):
     """Pure-python loop restatement (small cases).  Returns ids int32[n,T] (-1 pad),
     counts int32[n,T], w64 float64[n,T], nvalid int32[n] (+ trace int32[n,W,L])."""

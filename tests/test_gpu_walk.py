@@ -140,7 +140,7 @@ def test_walk_index_structure_and_deep_rows(K, leaf_format, monkeypatch):
     deep enough for 3-4 tree levels (degree up to 5000) searched identically to the flat binary
     search."""
     from mre_b200 import _native as NV
-    monkeypatch.setenv("PB200_WALK_LEAF", "wide" if leaf_format == "wide" else "auto")
+    monkeypatch.setenv("PB200_WALK_LEAF", leaf_format)
     rng = np.random.Generator(np.random.PCG64(3))
     degs = [0, 1, 7, 8, 9, 63, 64, 65, 511, 512, 513, 4097, 5000]
     src = np.concatenate([np.full(d, v) for v, d in enumerate(degs)]).astype(np.int64)
@@ -197,10 +197,11 @@ def test_walk_index_structure_and_deep_rows(K, leaf_format, monkeypatch):
         np.testing.assert_array_equal(_np(a), o[key])
 
 
-def test_compact_leaf_falls_back_to_wide_for_heavy_blocks(K):
+def test_compact_leaf_falls_back_to_wide_for_heavy_blocks(K, monkeypatch):
     """Blocks spanning more than 255 weight quanta (or >= 2^24 nodes) cannot use the 32-byte leaf:
     the builder must pick the 64-byte format and the walks must still match the flat search."""
     from mre_b200 import _native as N
+    monkeypatch.setenv("PB200_WALK_LEAF", "compact")
     rng = np.random.Generator(np.random.PCG64(8))
     n_edges = 4000
     src = rng.integers(0, 50, n_edges).astype(np.int64)
@@ -213,3 +214,59 @@ def test_compact_leaf_falls_back_to_wide_for_heavy_blocks(K):
     b = K.walk_topt(csr, torch.arange(50), 64, 3, 8, 5, 0, return_trace=True, use_index=False)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(_np(x), _np(y))
+
+
+def _deep_graph(rng, degs, wmax, N=6000):
+    src = np.concatenate([np.full(d, v) for v, d in enumerate(degs)]).astype(np.int64)
+    dst = rng.integers(0, len(degs), size=src.size).astype(np.int64)
+    w = (0.5 * rng.integers(1, wmax + 1, size=src.size)).astype(np.float32)      # no zero weights
+    perm = rng.permutation(src.size)
+    return np.stack([src[perm], dst[perm]]), w[perm]
+
+
+@pytest.mark.parametrize("wmax", [1, 10, 120])
+def test_bucket_index_structure_and_walks(K, wmax):
+    """The direct-addressed bucket index (default): meta and every 32-byte bucket equal the numpy
+    restatement of the format, and walks through it -- lean kernel (W*L <= 200, with and without
+    trace, L = 2 and generic L) and the generic kernel (larger W*L) -- equal the flat search and the C oracle."""
+    from mre_b200 import _native as NV
+    rng = np.random.Generator(np.random.PCG64(30 + wmax))
+    degs = [0, 1, 7, 8, 9, 63, 64, 65, 511, 512, 513, 4097, 5000]
+    ei, w = _deep_graph(rng, degs, wmax)
+    N = 6000
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=N)
+    assert csr.leaf_format == NV.LEAF_BUCKET and csr.idx is None
+    row_ptr, col, cum = O.csr_build(ei, w, N, 1)
+    meta, leaf = O.walk_bucket_index(row_ptr, col, cum)
+    got_meta = _np(csr.meta).view(np.uint32)
+    has = meta[:, 1] > 0
+    np.testing.assert_array_equal(got_meta[:, 1:], meta[:, 1:])
+    np.testing.assert_array_equal(got_meta[has, 0], meta[has, 0])
+    np.testing.assert_array_equal(np.ascontiguousarray(_np(csr.leaf)).view(np.uint8).reshape(-1, 32), leaf)
+    starts = np.arange(len(degs))
+    for (W, L, T) in [(100, 2, 10), (64, 3, 8), (200, 3, 20), (33, 1, 32), (7, 5, 3)]:
+        got = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 77, 3, return_trace=True)
+        flat = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 77, 3, return_trace=True, use_index=False)
+        o = O.c_walk_topt(row_ptr, col, cum, starts, W, L, T, 77, 3, return_trace=True)
+        for a, b, key in zip(got, flat, ["ids", "counts", "w32", "nvalid", "trace"]):
+            np.testing.assert_array_equal(_np(a), _np(b))
+            np.testing.assert_array_equal(_np(a), o[key])
+        notrace = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 77, 3)
+        for a, b in zip(notrace, got[:4]):
+            np.testing.assert_array_equal(_np(a), _np(b))
+
+
+def test_bucket_index_fallbacks(K):
+    """Graphs the bucket format does not cover keep the tree index: a zero-weight edge, weights so
+    heavy that buckets would dwarf the edge list.  An explicit request raises."""
+    from mre_b200 import _native as NV
+    rng = np.random.Generator(np.random.PCG64(9))
+    ei, w = _deep_graph(rng, [5, 40, 300], 10, N=400)
+    w0 = w.copy(); w0[3] = 0.0
+    assert K.csr_build(torch.from_numpy(ei), torch.from_numpy(w0), num_nodes=400).leaf_format != NV.LEAF_BUCKET
+    heavy = (w * 4096).astype(np.float32)
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(heavy), num_nodes=400)
+    assert csr.leaf_format != NV.LEAF_BUCKET and csr.meta is not None
+    with pytest.raises(NV.NativeError):
+        K.csr_build(torch.from_numpy(ei), torch.from_numpy(w0), num_nodes=400, index="bucket")
+    assert K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=400).leaf_format == NV.LEAF_BUCKET

@@ -1,7 +1,10 @@
-"""Times the walk kernel variants (PB200_WALK_VARIANT) on config C2 in separate processes:
-bit1 = binary in-node search, bit2 = register top-T selection,
-bits 4.. = min resident blocks per SM (register cap).  Usage: python tools/tune_walk.py [variants...]"""
-import os, subprocess, sys, time
+"""Times the walk kernel on config C2 in separate processes, one per variant.
+A variant is LEAF[:MINBLOCKS[:OLDVARIANT]] -- LEAF in bucket / compact / wide (PB200_WALK_LEAF),
+MINBLOCKS = resident blocks per SM the lean bucket kernel is compiled for (PB200_WALK_MINBLOCKS),
+OLDVARIANT = PB200_WALK_VARIANT of the tree-index kernel.  Prints mean / min ms per launch and a
+checksum of the outputs (must be identical across variants: all of them are bit-exact).
+Usage: python tools/tune_walk.py [variants...]"""
+import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import sys, time, numpy as np, torch
@@ -9,7 +12,9 @@ sys.path.insert(0, %r)
 import mre_b200
 from mre_b200 import kernels as K
 d = np.load("/tmp/c2_graph.npz")
+t0 = time.time()
 csr = K.csr_build(torch.from_numpy(d["ei"]), torch.from_numpy(d["w"]), num_nodes=int(d["N"]))
+torch.cuda.synchronize(); t_build = time.time() - t0
 nodes = torch.arange(62423, dtype=torch.int32, device="cuda")
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 for _ in range(3): K.walk_topt(csr, nodes, 100, 2, 10, 1234, 0)
@@ -19,8 +24,9 @@ for e in range(10):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); out = K.walk_topt(csr, nodes, 100, 2, 10, 1234, e); b.record()
     torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
-chk = int(out[0].long().sum()) ^ int(out[1].long().sum())
-print("variant", %s, "walk_ms mean %%.4f min %%.4f chk %%d" %% (np.mean(ts), np.min(ts), chk), flush=True)
+chk = int(out[0].long().sum()) ^ (int(out[1].long().sum()) << 20) ^ int((out[2].double() * 1e6).sum().item())
+print("variant", %r, "walk_ms mean %%.4f min %%.4f chk %%d index_MB %%.0f fmt %%d build_s %%.2f" %% (
+    np.mean(ts), np.min(ts), chk, csr.index_nbytes() / 1e6, csr.leaf_format, t_build), flush=True)
 '''
 if not os.path.exists("/tmp/c2_graph.npz"):
     sys.path.insert(0, ROOT)
@@ -29,8 +35,13 @@ if not os.path.exists("/tmp/c2_graph.npz"):
     M, U, R = S.CONFIGS["C2"][:3]
     ei, w = S.bipartite_graph(M, U, R, seed=0)
     np.savez("/tmp/c2_graph.npz", ei=ei, w=w, N=M + U)
-variants = sys.argv[1:] or ["0", "1", "2", "4", "6", "7", "80", "86", "96", "102"]
+variants = sys.argv[1:] or ["bucket:6", "bucket:8", "bucket:7", "bucket:5", "compact"]
 for v in variants:
-    env = dict(os.environ, PB200_WALK_VARIANT=v)
+    parts = v.split(":")
+    env = dict(os.environ, PB200_WALK_LEAF=parts[0])
+    if len(parts) > 1 and parts[1]:
+        env["PB200_WALK_MINBLOCKS"] = parts[1]
+    if len(parts) > 2:
+        env["PB200_WALK_VARIANT"] = parts[2]
     r = subprocess.run([sys.executable, "-c", CHILD % (ROOT, v)], env=env, capture_output=True, text=True, timeout=300)
-    print((r.stdout.strip() or r.stderr.strip()[-300:]), flush=True)
+    print((r.stdout.strip() or r.stderr.strip()[-600:]), flush=True)
