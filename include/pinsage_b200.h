@@ -43,6 +43,12 @@ const char* pb200_last_error(void);
 /* number of kernel launches issued by this library on the calling process so far
  * (bench.py reports the delta over the timed region as "gpu_launches") */
 int64_t pb200_launch_count(void);
+/* Device-wide L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes; the
+ * CUDA default is 64).  The walk kernel fetches one random 32-byte block per step: at 64 every miss
+ * moves two DRAM sectors.  Affects every kernel of the process on the current device; the Python
+ * mirror sets 32 when a RandomWalkSampler is built unless PB200_L2_FETCH overrides it. */
+int pb200_set_l2_fetch_granularity(int bytes);
+int pb200_get_l2_fetch_granularity(void);
 
 /* ------------------------------------------------------------------------------------
  * S0  RandomWalkSampler.__init__/_prepare_adjacency_list   (utils/random_walk.py:11-50)

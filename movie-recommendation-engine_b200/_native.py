@@ -24,6 +24,8 @@ SIGNATURES = {
     "pb200_abi_version": (c_int, []),
     "pb200_last_error": (ctypes.c_char_p, []),
     "pb200_launch_count": (c_i64, []),
+    "pb200_set_l2_fetch_granularity": (c_int, [c_int]),
+    "pb200_get_l2_fetch_granularity": (c_int, []),
     "pb200_edge_weight_probe": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "pb200_csr_build_workspace_bytes": (c_size, [c_i64, c_i64]),
     "pb200_csr_build": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr,

@@ -435,52 +435,109 @@ __device__ __forceinline__ Philox4 philox_keys(uint32_t c0, uint32_t c1, uint32_
     return o;
 }
 
-// All 32 lanes call; lanes with !alive only take part in the votes.  256 slots.
+// ---- visit table: 256 slots x {key, count, first}, hardware shared-memory atomics -----------------
+// All 32 lanes call; lanes with !alive only take part in the votes.  kIns selects the probe loop:
+//   0  vote-terminated loop, bool flag            (first working version, 0.208 ms at C2)
+//   3  vote-terminated loop, the slot register doubles as the "pending" flag
+//   4  plain divergent loop closed by __syncwarp
+// Measured and rejected (tools/tune_walk.py, gpurun_out/r2_tune2.log; tools/ubench_smem.cu): an
+// atomics-free table -- lanes visiting the same node grouped by match.any, the group leader inserting
+// with plain stores + write-then-verify -- 0.225 ms (256 slots) / 0.330 ms (512 slots: occupancy):
+// match.any with 32 distinct values costs 64 cycles of issue per warp and 383 cycles of latency on
+// B200, an ATOMS.CAS / ADD / MIN with spread addresses 7 / 3.5 / 2.7 cycles.
+template <int kIns>
 __device__ __forceinline__ void table_insert_uniform(int32_t* keys, int node, bool alive, uint32_t fs) {
     const uint32_t hh = (uint32_t)node * 2654435761u;
-    uint32_t h = hh >> 24;
     const uint32_t step = ((hh >> 8) & 0xFEu) | 1u;      // odd: visits every slot of the 2^8 table
-    bool pending = alive;
-    while (__any_sync(kFull, pending)) {
-        if (pending) {
-            const int prev = atomicCAS(&keys[h], kEmpty, node);
-            if (prev == kEmpty || prev == node) pending = false;
-            else h = (h + step) & 255u;
+    uint32_t slot;
+    if (kIns == 0) {
+        uint32_t h = hh >> 24;
+        bool pending = alive;
+        while (__any_sync(kFull, pending)) {
+            if (pending) {
+                const int prev = atomicCAS(&keys[h], kEmpty, node);
+                if (prev == kEmpty || prev == node) pending = false;
+                else h = (h + step) & 255u;
+            }
         }
+        slot = h;
+    } else if (kIns == 3) {
+        int h = alive ? (int)(hh >> 24) : -1;             // h < 0: nothing (left) to do
+        slot = 0;
+        while (__any_sync(kFull, h >= 0)) {
+            if (h >= 0) {
+                const int prev = atomicCAS(&keys[h], kEmpty, node);
+                const bool hit = prev == kEmpty || prev == node;
+                slot = hit ? (uint32_t)h : slot;
+                h = hit ? -1 : (int)(((uint32_t)h + step) & 255u);
+            }
+        }
+    } else {
+        uint32_t h = hh >> 24;
+        if (alive) {
+            for (;;) {
+                const int prev = atomicCAS(&keys[h], kEmpty, node);
+                if (prev == kEmpty || prev == node) break;
+                h = (h + step) & 255u;
+            }
+        }
+        __syncwarp();
+        slot = h;
     }
     if (alive) {
-        atomicAdd(reinterpret_cast<uint32_t*>(keys) + 256 + h, 1u);
-        atomicMin(reinterpret_cast<uint32_t*>(keys) + 512 + h, fs);
+        atomicAdd(reinterpret_cast<uint32_t*>(keys) + 256 + slot, 1u);
+        atomicMin(reinterpret_cast<uint32_t*>(keys) + 512 + slot, fs);
     }
 }
 
-// Register top-T for the 256-slot table (see select_topt_regs); fp32 division for the weights.
-__device__ __forceinline__ void select_topt_fast(const WalkParams& p, const int32_t* keys, int64_t s, int lane) {
-    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(keys) + 256;
-    const uint32_t* first = cnt + 256;
+// Register top-T for the lean kernel's table (see select_topt_regs); fp32 division for the weights.
+// kSel 0: the winner of a round shifts its 8 sorted keys down in registers; 1: the sorted keys go back
+// to the lane's own (now dead) count words and the lane keeps a head pointer.
+template <int kSel>
+__device__ __forceinline__ void select_topt_fast(const WalkParams& p, int32_t* keys, int64_t s, int lane) {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(keys) + 256;
     uint32_t k[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int slot = i * 32 + lane;
         const uint32_t c = cnt[slot];
-        k[i] = c ? ((c << 17) | ((255u - first[slot]) << 9) | (uint32_t)slot) : 0u;
+        k[i] = c ? ((c << 17) | ((255u - cnt[256 + slot]) << 9) | (uint32_t)slot) : 0u;
     }
     sort8_desc(k);
     int my_id = -1; uint32_t my_cnt = 0, total = 0;
     int nvalid = 0;
-    for (int j = 0; j < p.T; ++j) {
-        const uint32_t m = __reduce_max_sync(kFull, k[0]);
-        if (m == 0) break;                     // warp-uniform: fewer than T distinct nodes
-        const bool win = k[0] == m;            // keys are unique (slot bits)
+    if (kSel == 1) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) k[i] = win ? k[i + 1] : k[i];
-        k[7] = win ? 0u : k[7];
-        const uint32_t c = m >> 17;
-        const int node = keys[m & 255u];       // broadcast
-        total += c;
-        my_id = lane == j ? node : my_id;
-        my_cnt = lane == j ? c : my_cnt;
-        ++nvalid;
+        for (int i = 1; i < 8; ++i) cnt[i * 32 + lane] = k[i];      // only this lane reads these words
+        cnt[256 + lane] = 0u;                                       // sentinel after the 8th key
+        uint32_t head = k[0];
+        uint32_t* nxt = cnt + 32 + lane;
+        for (int j = 0; j < p.T; ++j) {
+            const uint32_t m = __reduce_max_sync(kFull, head);
+            if (m == 0) break;
+            if (head == m) { head = *nxt; nxt += 32; }
+            const uint32_t c = m >> 17;
+            const int node = keys[m & 255u];   // broadcast
+            total += c;
+            my_id = lane == j ? node : my_id;
+            my_cnt = lane == j ? c : my_cnt;
+            ++nvalid;
+        }
+    } else {
+        for (int j = 0; j < p.T; ++j) {
+            const uint32_t m = __reduce_max_sync(kFull, k[0]);
+            if (m == 0) break;                     // warp-uniform: fewer than T distinct nodes
+            const bool win = k[0] == m;            // keys are unique (slot bits)
+#pragma unroll
+            for (int i = 0; i < 7; ++i) k[i] = win ? k[i + 1] : k[i];
+            k[7] = win ? 0u : k[7];
+            const uint32_t c = m >> 17;
+            const int node = keys[m & 255u];       // broadcast
+            total += c;
+            my_id = lane == j ? node : my_id;
+            my_cnt = lane == j ? c : my_cnt;
+            ++nvalid;
+        }
     }
     if (lane < p.T) {
         const bool has = lane < nvalid;
@@ -492,7 +549,8 @@ __device__ __forceinline__ void select_topt_fast(const WalkParams& p, const int3
     if (lane == 0) p.out_nvalid[s] = nvalid;
 }
 
-template <int kL, bool kTrace, int kMinBlocks>
+// kVar = 10 * kSel + kIns
+template <int kL, bool kTrace, int kVar, int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const WalkParams p, const PhiloxKeys pk) {
     extern __shared__ int32_t smem[];
     const int lane = threadIdx.x & 31;
@@ -522,12 +580,12 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const Walk
                 if (alive) next = bucket_step(p.meta, p.leaf, cur, a, b);
                 if (kTrace) { if (walk < p.W) p.trace_out[(s * p.W + walk) * L + l] = next; }
                 alive = next >= 0;             // dead end: random_walk.py:68-69
-                table_insert_uniform(keys, next, alive, (uint32_t)(walk * L + l));
+                table_insert_uniform<kVar % 10>(keys, next, alive, (uint32_t)(walk * L + l));
                 cur = alive ? next : cur;
             }
         }
         __syncwarp();
-        select_topt_fast(p, keys, s, lane);
+        select_topt_fast<kVar / 10>(p, keys, s, lane);
         __syncwarp();
     }
 }
@@ -537,30 +595,43 @@ static void philox_round_keys(uint32_t seed_lo, uint32_t seed_hi, PhiloxKeys& k)
     for (int r = 0; r < 10; ++r) { k.k0[r] = k0; k.k1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
 }
 
-template <int kL, bool kTrace, int kMinBlocks>
+template <int kL, bool kTrace, int kVar, int kMinBlocks>
 static int launch_bucket_variant(const WalkParams& p, const PhiloxKeys& pk, cudaStream_t stream) {
     int64_t blocks = ceil_div(p.n, (int64_t)8);
     const int64_t cap = (int64_t)kSMs * 32;
     if (blocks > cap) blocks = cap;
-    walk_bucket_kernel<kL, kTrace, kMinBlocks><<<(unsigned)blocks, 256, 8 * 768 * sizeof(int32_t), stream>>>(p, pk);
+    static const int pad = [] { const char* e = getenv("PB200_WALK_PAD"); return e ? atoi(e) : 0; }();   // occupancy experiments
+    const size_t smem = 8 * 768 * sizeof(int32_t) + (size_t)pad;
+    if (smem > 48 * 1024)
+        PB_CUDA(cudaFuncSetAttribute(walk_bucket_kernel<kL, kTrace, kVar, kMinBlocks>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    walk_bucket_kernel<kL, kTrace, kVar, kMinBlocks><<<(unsigned)blocks, 256, smem, stream>>>(p, pk);
     return check_launch("walk_bucket_kernel");
 }
 
 // W*L <= 200 visits in a 256-slot table (load <= 0.78), first-visit index < 255, T <= 32
 static bool bucket_fast_ok(const WalkParams& p) { return p.W * p.L <= 200 && p.T <= 32; }
 
+#ifndef PB200_WALK_TABLE_DEFAULT
+#define PB200_WALK_TABLE_DEFAULT 0
+#endif
 static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
+    // tuning knobs (tools/tune_walk.py): PB200_WALK_MINBLOCKS = 6 | 7 | 8 (register cap),
+    // PB200_WALK_TABLE = 10 * select version + insert version
     static const int minb = [] { const char* e = getenv("PB200_WALK_MINBLOCKS"); return e ? atoi(e) : 6; }();
+    static const int var = [] { const char* e = getenv("PB200_WALK_TABLE"); return e ? atoi(e) : PB200_WALK_TABLE_DEFAULT; }();
     PhiloxKeys pk;
     philox_round_keys(p.seed_lo, p.seed_hi, pk);
-#define PB_B(L_, T_) do { if (minb == 8) return launch_bucket_variant<L_, T_, 8>(p, pk, stream); \
-                          if (minb == 7) return launch_bucket_variant<L_, T_, 7>(p, pk, stream); \
-                          if (minb == 5) return launch_bucket_variant<L_, T_, 5>(p, pk, stream); \
-                          return launch_bucket_variant<L_, T_, 6>(p, pk, stream); } while (0)
+#define PB_B3(L_, T_, V_) do { if (minb == 7) return launch_bucket_variant<L_, T_, V_, 7>(p, pk, stream); \
+                               if (minb == 8) return launch_bucket_variant<L_, T_, V_, 8>(p, pk, stream); \
+                               return launch_bucket_variant<L_, T_, V_, 6>(p, pk, stream); } while (0)
+#define PB_B(L_, T_) do { if (var == 3) PB_B3(L_, T_, 3); if (var == 4) PB_B3(L_, T_, 4); if (var == 13) PB_B3(L_, T_, 13); \
+                          if (var == 14) PB_B3(L_, T_, 14); if (var == 10) PB_B3(L_, T_, 10); PB_B3(L_, T_, 0); } while (0)
     if (p.trace_out) { if (p.L == 2) PB_B(2, true); PB_B(0, true); }
     if (p.L == 2) PB_B(2, false);
     PB_B(0, false);
 #undef PB_B
+#undef PB_B3
 }
 
 // Measured and rejected (B200, config C2, tools/tune_walk.py; baseline 0.360 ms per launch):
