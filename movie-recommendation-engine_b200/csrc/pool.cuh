@@ -30,8 +30,10 @@ __device__ __forceinline__ int prepare_list(const ListArgs& a, int64_t row, int*
     for (int base = 0; base < len; base += 32) {
         const int j = base + lane;
         const int id = j < len ? ids_row[j] : -1;
-        // pinsage.py:124 (idx <= max_idx) / layers.py:109 (n < x.size(0)); negative ids are
-        // undefined behaviour in the reference (python wrap-around) and are dropped here.
+        // pinsage.py:124 (idx <= max_idx) / layers.py:109 (n < x.size(0)).  Negative ids index from the
+        // end in the reference (python semantics): the host mirror rewrites them to id + num_rows (or
+        // raises IndexError below -num_rows) before the lists reach the device
+        // (neighbor_lists._wrap_negative); a negative id that still arrives here is padding.
         const bool valid = j < len && id >= 0 && (int64_t)id < a.num_rows;
         const unsigned m = __ballot_sync(kFull, valid);
         const int rank = nv + __popc(m & ((1u << lane) - 1u));

@@ -192,10 +192,47 @@ __device__ __forceinline__ int indexed_step(const uint4* __restrict__ meta,
 // (a, b) are the two Philox words of this step: k53 = (a >> 5) * 2^26 + (b >> 6) (uniform53),
 // t = floor(k53 * S / 2^53) = (kh * S + mulhi(kl, S)) >> 21 with kh = k53 >> 32, kl = low word
 // (floor(floor(x / 2^32) / 2^21) = floor(x / 2^53); kh * S * 2^32 is a multiple of 2^32).
+// kLd: cache behaviour of the two divergent loads.  0: ld.global.nc (+ L2 evict_first on the bucket);
+// 1: + L1::no_allocate; 2: ld.global.cg (L2 only); 3: L1::evict_first.  (L1 has no reuse to offer
+// here -- 3 % hit rate -- but every outstanding divergent load pins one of its 128-byte lines.)
+template <int kLd>
+__device__ __forceinline__ U8 ld256_bucket(const uint32_t* p) {
+    U8 r;
+    if (kLd == 1)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                       "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    else if (kLd == 2)
+        asm volatile("ld.global.cg.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                       "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    else if (kLd == 3)
+        asm volatile("ld.global.nc.L1::evict_first.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                       "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    else
+        r = ld256_stream(p);
+    return r;
+}
+template <int kLd>
+__device__ __forceinline__ uint4 ld_meta(const uint4* p) {
+    uint4 r;
+    if (kLd == 1)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (kLd == 2)
+        asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (kLd == 3)
+        asm volatile("ld.global.nc.L1::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else
+        r = __ldg(p);
+    return r;
+}
+
+template <int kLd = 0>
 __device__ __forceinline__ int bucket_step(const uint4* __restrict__ meta,
                                            const uint32_t* __restrict__ leaf, int cur, uint32_t a,
                                            uint32_t b) {
-    const uint4 m = __ldg(meta + cur);   // {first bucket, degree, row total S, shift s}
+    const uint4 m = ld_meta<kLd>(meta + cur);   // {first bucket, degree, row total S, shift s}
     if (m.y == 0u) return -1;
     const uint32_t kh = a >> 11;
     const uint32_t kl = ((a >> 5) << 26) | (b >> 6);
@@ -203,9 +240,57 @@ __device__ __forceinline__ int bucket_step(const uint4* __restrict__ meta,
     const uint32_t t = (uint32_t)(prod >> 21);
     const uint32_t j = t >> m.w;
     const uint32_t tr = t - (j << m.w);
-    const U8 w = ld256_stream(leaf + ((size_t)(m.x + j) << 3));
+    const U8 w = ld256_bucket<kLd>(leaf + ((size_t)(m.x + j) << 3));
     // slots with rel <= tr, bytewise: 0x80 + tr - rel keeps bit 7 iff rel <= tr (rel <= 128, tr <= 127:
     // no borrow crosses a byte).  rel is ascending and the edge holding t is in the bucket: c <= 7.
+    const uint32_t t4 = tr * 0x01010101u + 0x80808080u;
+    const uint32_t c = (uint32_t)(__popc((t4 - w.v[0]) & 0x80808080u) + __popc((t4 - w.v[1]) & 0x80808080u));
+    const uint32_t r0 = __byte_perm(w.v[2], w.v[3], c);
+    const uint32_t r1 = __byte_perm(w.v[4], w.v[5], c);
+    const uint32_t r2 = __byte_perm(w.v[6], w.v[7], c);
+    return (int)(__byte_perm(__byte_perm(r0, r1, 0x0040u), r2, 0x0410u) & 0x00FFFFFFu);
+}
+
+// Predicated forms for the batched kernel: kB independent walks per lane are kept in flight, their
+// loads issued back to back (no branch may separate them), so a lane that has nothing to do must
+// not fetch.  mode: 0 = ld.global.nc, 2 = ld.global.cg (L2 only).
+template <int kLd>
+__device__ __forceinline__ uint4 ld_meta_if(const uint4* p, bool on) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (kLd == 2)
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4]; }"
+                     : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((uint32_t)on));
+    else
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4]; }"
+                     : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((uint32_t)on));
+    return r;
+}
+template <int kLd>
+__device__ __forceinline__ U8 ld256_bucket_if(const uint32_t* p, bool on) {
+    U8 r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0u;
+    if (kLd == 2)
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %9, 0; @q ld.global.cg.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8]; }"
+                     : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]),
+                       "+r"(r.v[6]), "+r"(r.v[7]) : "l"(p), "r"((uint32_t)on));
+    else
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %9, 0; @q ld.global.nc.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8]; }"
+                     : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]),
+                       "+r"(r.v[6]), "+r"(r.v[7]) : "l"(p), "r"((uint32_t)on));
+    return r;
+}
+// bucket_step in two halves: address of the bucket + in-bucket threshold, then the pick
+__device__ __forceinline__ uint32_t bucket_locate(const uint4& m, uint32_t a, uint32_t b, uint32_t& tr) {
+    const uint32_t kh = a >> 11;
+    const uint32_t kl = ((a >> 5) << 26) | (b >> 6);
+    const uint64_t prod = (uint64_t)kh * m.z + (uint64_t)__umulhi(kl, m.z);
+    const uint32_t t = (uint32_t)(prod >> 21);
+    const uint32_t j = t >> m.w;
+    tr = t - (j << m.w);
+    return m.x + j;
+}
+__device__ __forceinline__ int bucket_pick(const U8& w, uint32_t tr) {
     const uint32_t t4 = tr * 0x01010101u + 0x80808080u;
     const uint32_t c = (uint32_t)(__popc((t4 - w.v[0]) & 0x80808080u) + __popc((t4 - w.v[1]) & 0x80808080u));
     const uint32_t r0 = __byte_perm(w.v[2], w.v[3], c);
@@ -490,6 +575,44 @@ __device__ __forceinline__ void table_insert_uniform(int32_t* keys, int node, bo
     }
 }
 
+// kB visits per lane in ONE probe loop: the loop runs max (not sum) of the probe counts, and the vote /
+// branch overhead is paid once per iteration for all kB items.  Order does not matter: counts are
+// atomicAdd, first visits atomicMin.
+template <int kB>
+__device__ __forceinline__ void table_insert_multi(int32_t* keys, const int (&node)[kB], const bool (&alive)[kB],
+                                                   const uint32_t (&fs)[kB]) {
+    int h[kB]; uint32_t step[kB], slot[kB];
+    int all = -1;
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+        const uint32_t hh = (uint32_t)node[i] * 2654435761u;
+        step[i] = ((hh >> 8) & 0xFEu) | 1u;
+        h[i] = alive[i] ? (int)(hh >> 24) : -1;           // h < 0: nothing (left) to do
+        slot[i] = 0;
+        all &= h[i];
+    }
+    while (__any_sync(kFull, all >= 0)) {                 // some h[i] >= 0
+        all = -1;
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            if (h[i] >= 0) {
+                const int prev = atomicCAS(&keys[h[i]], kEmpty, node[i]);
+                const bool hit = prev == kEmpty || prev == node[i];
+                slot[i] = hit ? (uint32_t)h[i] : slot[i];
+                h[i] = hit ? -1 : (int)(((uint32_t)h[i] + step[i]) & 255u);
+            }
+            all &= h[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+        if (alive[i]) {
+            atomicAdd(reinterpret_cast<uint32_t*>(keys) + 256 + slot[i], 1u);
+            atomicMin(reinterpret_cast<uint32_t*>(keys) + 512 + slot[i], fs[i]);
+        }
+    }
+}
+
 // Register top-T for the lean kernel's table (see select_topt_regs); fp32 division for the weights.
 // kSel 0: the winner of a round shifts its 8 sorted keys down in registers; 1: the sorted keys go back
 // to the lane's own (now dead) count words and the lane keeps a head pointer.
@@ -549,7 +672,7 @@ __device__ __forceinline__ void select_topt_fast(const WalkParams& p, int32_t* k
     if (lane == 0) p.out_nvalid[s] = nvalid;
 }
 
-// kVar = 10 * kSel + kIns
+// kVar = 100 * kLd (steps after the first) + 10 * kSel + kIns
 template <int kL, bool kTrace, int kVar, int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const WalkParams p, const PhiloxKeys pk) {
     extern __shared__ int32_t smem[];
@@ -577,7 +700,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const Walk
                     r = philox_keys((uint32_t)start, (uint32_t)walk, (uint32_t)(l >> 1), epoch, pk);
                 const uint32_t a = (l & 1) ? r.v[2] : r.v[0], b = (l & 1) ? r.v[3] : r.v[1];
                 int next = -1;
-                if (alive) next = bucket_step(p.meta, p.leaf, cur, a, b);
+                if (alive) next = l == 0 ? bucket_step<0>(p.meta, p.leaf, cur, a, b)
+                                          : bucket_step<kVar / 100>(p.meta, p.leaf, cur, a, b);
                 if (kTrace) { if (walk < p.W) p.trace_out[(s * p.W + walk) * L + l] = next; }
                 alive = next >= 0;             // dead end: random_walk.py:68-69
                 table_insert_uniform<kVar % 10>(keys, next, alive, (uint32_t)(walk * L + l));
@@ -585,7 +709,67 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const Walk
             }
         }
         __syncwarp();
-        select_topt_fast<kVar / 10>(p, keys, s, lane);
+        select_topt_fast<(kVar / 10) % 10>(p, keys, s, lane);
+        __syncwarp();
+    }
+}
+
+// Batched form: kB walks per lane in flight (walks lane, lane + 32, ...).  The one-walk-per-lane kernel
+// above is LATENCY bound once the step is this short (r2 measurements, tools/tune_walk.py: time =
+// 23 us + 54 us per round of 32 walks, the 4-lane tail round of W = 100 alone 21 us; more resident
+// warps make it slower, not faster), so the independent walks of a start node are overlapped inside
+// the lane instead: all meta loads, then all bucket loads, then the picks and the table inserts.
+template <int kL, bool kTrace, int kLd, int kB, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_batched_kernel(const WalkParams p, const PhiloxKeys pk) {
+    extern __shared__ int32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int32_t* keys = smem + warp * 768;                  // [keys | cnt | first] x 256 slots
+    const int L = kL ? kL : p.L;
+    const uint32_t epoch = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
+    for (int64_t s = (int64_t)blockIdx.x * 8 + warp; s < p.n; s += (int64_t)gridDim.x * 8) {
+        {
+            int4* k4 = reinterpret_cast<int4*>(keys) + lane * 2;
+            const int4 e = make_int4(-1, -1, -1, -1), z = make_int4(0, 0, 0, 0);
+            k4[0] = e; k4[1] = e; k4[64] = z; k4[65] = z; k4[128] = e; k4[129] = e;
+        }
+        __syncwarp();
+        const int start = __ldg(p.starts + s);
+        for (int base = 0; base < p.W; base += 32 * kB) {
+            int cur[kB]; bool alive[kB]; Philox4 r[kB];
+#pragma unroll
+            for (int i = 0; i < kB; ++i) { alive[i] = base + 32 * i + lane < p.W; cur[i] = start; }
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                if ((l & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < kB; ++i)
+                        r[i] = philox_keys((uint32_t)start, (uint32_t)(base + 32 * i + lane), (uint32_t)(l >> 1), epoch, pk);
+                }
+                uint4 m[kB];
+#pragma unroll
+                for (int i = 0; i < kB; ++i) m[i] = ld_meta_if<kLd>(p.meta + cur[i], alive[i]);
+                U8 w[kB]; uint32_t tr[kB];
+#pragma unroll
+                for (int i = 0; i < kB; ++i) {
+                    alive[i] = alive[i] && m[i].y != 0u;       // dead end: random_walk.py:68-69
+                    const uint32_t blk = bucket_locate(m[i], (l & 1) ? r[i].v[2] : r[i].v[0], (l & 1) ? r[i].v[3] : r[i].v[1], tr[i]);
+                    w[i] = ld256_bucket_if<kLd>(p.leaf + ((size_t)blk << 3), alive[i]);
+                }
+                int next[kB]; uint32_t fs[kB];
+#pragma unroll
+                for (int i = 0; i < kB; ++i) {
+                    const int walk = base + 32 * i + lane;
+                    next[i] = alive[i] ? bucket_pick(w[i], tr[i]) : -1;
+                    fs[i] = (uint32_t)(walk * L + l);
+                    if (kTrace) { if (walk < p.W) p.trace_out[(s * p.W + walk) * L + l] = next[i]; }
+                    cur[i] = alive[i] ? next[i] : cur[i];
+                }
+                table_insert_multi<kB>(keys, next, alive, fs);
+            }
+        }
+        __syncwarp();
+        select_topt_fast<1>(p, keys, s, lane);
         __syncwarp();
     }
 }
@@ -605,6 +789,10 @@ static int launch_bucket_variant(const WalkParams& p, const PhiloxKeys& pk, cuda
     if (smem > 48 * 1024)
         PB_CUDA(cudaFuncSetAttribute(walk_bucket_kernel<kL, kTrace, kVar, kMinBlocks>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const int carve = [] { const char* e = getenv("PB200_WALK_CARVE"); return e ? atoi(e) : -1; }();
+    if (carve >= 0)
+        PB_CUDA(cudaFuncSetAttribute(walk_bucket_kernel<kL, kTrace, kVar, kMinBlocks>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     walk_bucket_kernel<kL, kTrace, kVar, kMinBlocks><<<(unsigned)blocks, 256, smem, stream>>>(p, pk);
     return check_launch("walk_bucket_kernel");
 }
@@ -613,7 +801,10 @@ static int launch_bucket_variant(const WalkParams& p, const PhiloxKeys& pk, cuda
 static bool bucket_fast_ok(const WalkParams& p) { return p.W * p.L <= 200 && p.T <= 32; }
 
 #ifndef PB200_WALK_TABLE_DEFAULT
-#define PB200_WALK_TABLE_DEFAULT 0
+#define PB200_WALK_TABLE_DEFAULT 213
+#endif
+#ifndef PB200_WALK_BATCH_DEFAULT
+#define PB200_WALK_BATCH_DEFAULT 2
 #endif
 static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
     // tuning knobs (tools/tune_walk.py): PB200_WALK_MINBLOCKS = 6 | 7 | 8 (register cap),
@@ -622,11 +813,32 @@ static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
     static const int var = [] { const char* e = getenv("PB200_WALK_TABLE"); return e ? atoi(e) : PB200_WALK_TABLE_DEFAULT; }();
     PhiloxKeys pk;
     philox_round_keys(p.seed_lo, p.seed_hi, pk);
+    // PB200_WALK_BATCH = walks per lane in flight (0 = the one-walk kernel); PB200_WALK_LD = 0 | 2
+    static const int batch = [] { const char* e = getenv("PB200_WALK_BATCH"); return e ? atoi(e) : PB200_WALK_BATCH_DEFAULT; }();
+    static const int ld = [] { const char* e = getenv("PB200_WALK_LD"); return e ? atoi(e) : 2; }();
+    if (batch > 0) {
+        const int64_t cap = (int64_t)kSMs * 32;
+        int64_t blocks = ceil_div(p.n, (int64_t)8);
+        if (blocks > cap) blocks = cap;
+        const size_t smem = 8 * 768 * sizeof(int32_t);
+#define PB_BK(L_, T_, LD_, B_, M_) do { walk_bucket_batched_kernel<L_, T_, LD_, B_, M_><<<(unsigned)blocks, 256, smem, stream>>>(p, pk); \
+                                        return check_launch("walk_bucket_batched_kernel"); } while (0)
+#define PB_BB(L_, T_, LD_) do { if (batch == 2 && minb == 5) PB_BK(L_, T_, LD_, 2, 5); if (batch == 2) PB_BK(L_, T_, LD_, 2, 6); \
+                                if (batch == 4 && minb == 5) PB_BK(L_, T_, LD_, 4, 5); if (batch == 4 && minb == 3) PB_BK(L_, T_, LD_, 4, 3); \
+                                if (batch == 4) PB_BK(L_, T_, LD_, 4, 4); PB_BK(L_, T_, LD_, 1, 6); } while (0)
+#define PB_BL(L_, T_) do { if (ld == 0) PB_BB(L_, T_, 0); PB_BB(L_, T_, 2); } while (0)
+        if (p.trace_out) { if (p.L == 2) PB_BL(2, true); PB_BL(0, true); }
+        if (p.L == 2) PB_BL(2, false);
+        PB_BL(0, false);
+#undef PB_BL
+#undef PB_BB
+#undef PB_BK
+    }
 #define PB_B3(L_, T_, V_) do { if (minb == 7) return launch_bucket_variant<L_, T_, V_, 7>(p, pk, stream); \
                                if (minb == 8) return launch_bucket_variant<L_, T_, V_, 8>(p, pk, stream); \
                                return launch_bucket_variant<L_, T_, V_, 6>(p, pk, stream); } while (0)
-#define PB_B(L_, T_) do { if (var == 3) PB_B3(L_, T_, 3); if (var == 4) PB_B3(L_, T_, 4); if (var == 13) PB_B3(L_, T_, 13); \
-                          if (var == 14) PB_B3(L_, T_, 14); if (var == 10) PB_B3(L_, T_, 10); PB_B3(L_, T_, 0); } while (0)
+#define PB_B(L_, T_) do { if (var == 13) PB_B3(L_, T_, 13); if (var == 113) PB_B3(L_, T_, 113); if (var == 213) PB_B3(L_, T_, 213); \
+                          if (var == 313) PB_B3(L_, T_, 313); PB_B3(L_, T_, 0); } while (0)
     if (p.trace_out) { if (p.L == 2) PB_B(2, true); PB_B(0, true); }
     if (p.L == 2) PB_B(2, false);
     PB_B(0, false);

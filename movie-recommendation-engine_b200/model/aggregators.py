@@ -20,14 +20,19 @@ from .. import neighbor_lists as NL
 
 
 def _checked_lists(features, neighbors, weights, dev):
-    nb = NL.pad_lists(neighbors, weights, dev)
+    """``features[node_neighbors]`` semantics (reference :33, :71, :258): no filtering -- ids outside
+    [-M, M) raise IndexError, negative ids index from the end.  Checked on the host lists (no device
+    sync); a NeighborBatch of device tensors is checked on the device."""
     M = features.size(0)
+    if not isinstance(neighbors, NL.NeighborBatch):
+        return NL.pad_lists(neighbors, weights, dev, num_rows=M, check_upper=True)
+    nb = neighbors
     valid = torch.arange(nb.ids.size(1), device=dev)[None, :] < nb.list_len[:, None]
-    ids = nb.ids.to(torch.int64)
-    if bool(((ids >= M) & valid).any()) or bool(((ids < -M) & valid).any()):
+    if bool((((nb.ids >= M) | (nb.ids < -M)) & valid).any()):
         raise IndexError(f"index out of range for features with {M} rows")
-    if bool(((ids < 0) & valid).any()):      # python wrap-around semantics of features[list]
-        nb.ids = torch.where(valid & (nb.ids < 0), nb.ids + M, nb.ids)
+    if bool(((nb.ids < 0) & valid).any()):
+        nb = NL.NeighborBatch(torch.where(valid & (nb.ids < 0), nb.ids + M, nb.ids), nb.weights,
+                              nb.list_len, nb.weight_len)
     return nb
 
 

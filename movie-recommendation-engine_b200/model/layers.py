@@ -73,7 +73,7 @@ class GraphConvLayer(nn.Module):
 def _pool(x, neighbors, weights, mode):
     dev = N.device_of(x)
     xd = N.dev_tensor(x, torch.float32, dev)
-    nb = NL.pad_lists(neighbors, weights, dev)
+    nb = NL.pad_lists(neighbors, weights, dev, num_rows=xd.size(0))
     out = K.pool(xd, *nb.as_args(), mode)
     return out if x.is_cuda else out.to(x.device)
 

@@ -55,7 +55,7 @@ class ImportancePooling(nn.Module):
     def forward(self, x, neighbors, weights=None):
         dev = N.device_of(x)
         xd = N.dev_tensor(x, torch.float32, dev)
-        nb = NL.pad_lists(neighbors, weights, dev, bare_int=True)
+        nb = NL.pad_lists(neighbors, weights, dev, bare_int=True, num_rows=xd.size(0))
         out = K.pool(xd, *nb.as_args(), N.POOL_PINSAGE)
         return out if not isinstance(x, torch.Tensor) or x.is_cuda else out.to(x.device)
 
@@ -133,11 +133,12 @@ class PinSage(nn.Module):
             for i in range(self.num_layers):                                               # :222-240
                 if per_layer and len(sampled_neighbors) > i:
                     nb = sampled_neighbors[i] if tensor_path else \
-                        NL.pad_lists(sampled_neighbors[i], importance_weights[i], dev, bare_int=True)
+                        NL.pad_lists(sampled_neighbors[i], importance_weights[i], dev, bare_int=True,
+                                     num_rows=h.size(0))
                 else:                                                                      # :226-229
                     if shared is None:
                         shared = NL.pad_lists(sampled_neighbors, importance_weights, dev,
-                                              bare_int=True)
+                                              bare_int=True, num_rows=h.size(0))
                     nb = shared
                 if len(nb) != h.size(0):
                     raise RuntimeError(f"layer {i}: {len(nb)} neighbour lists for {h.size(0)} rows "

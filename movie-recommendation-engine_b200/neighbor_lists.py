@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 _I32_MAX = np.iinfo(np.int32).max
+_I32_MIN = np.iinfo(np.int32).min
 
 
 @dataclass
@@ -40,16 +41,33 @@ def _ragged_to_padded(rows, dtype, fill):
         flat = np.fromiter(chain.from_iterable(rows), dtype=np.float64 if dtype == np.float32
                            else np.int64, count=total)
         if dtype == np.int32:
-            flat = np.clip(flat, -1, _I32_MAX)        # ids beyond int32 are out of range anyway
+            flat = np.clip(flat, _I32_MIN, _I32_MAX)  # ids beyond int32 are out of range either way
         r = np.repeat(np.arange(len(rows)), lens)
         c = np.arange(total) - np.repeat(np.cumsum(lens) - lens, lens)
         out[r, c] = flat.astype(dtype)
     return out, lens.astype(np.int32)
 
 
-def pad_lists(neighbors, weights, device, bare_int=False):
+def _wrap_negative(ids, lens, num_rows, check_upper):
+    """Python indexing semantics of the reference's ``x[list_of_ids]`` on the host copy of the lists:
+    an id in [-num_rows, -1] addresses row id + num_rows, an id below -num_rows raises IndexError
+    (model/pinsage.py:146, model/layers.py:119/181/227, model/aggregators.py:33/71/258).  Every
+    validity filter of the reference (``idx <= max_idx``, ``n < x.size(0)``) lets negative ids
+    through.  check_upper: the aggregators do not filter at all, so ids >= num_rows raise too."""
+    valid = np.arange(ids.shape[1])[None, :] < lens[:, None]
+    neg = valid & (ids < 0)
+    if (neg & (ids < -num_rows)).any() or (check_upper and (valid & (ids >= num_rows)).any()):
+        raise IndexError(f"index out of range for a matrix with {num_rows} rows")
+    if neg.any():
+        ids = np.where(neg, ids + num_rows, ids).astype(np.int32)
+    return ids
+
+
+def pad_lists(neighbors, weights, device, bare_int=False, num_rows=None, check_upper=False):
     """Host lists -> NeighborBatch on `device`.  ``zip`` semantics: rows = min(len(n), len(w)).
-    bare_int=True applies model/pinsage.py:110-112 (an int entry means [int] with weight 1)."""
+    bare_int=True applies model/pinsage.py:110-112 (an int entry means [int] with weight 1).
+    num_rows: rows of the matrix the ids index; negative ids then follow Python indexing
+    (see _wrap_negative).  Without it negative ids are dropped by the kernels."""
     if isinstance(neighbors, NeighborBatch):
         return neighbors
     n = len(neighbors) if weights is None else min(len(neighbors), len(weights))
@@ -62,6 +80,8 @@ def pad_lists(neighbors, weights, device, bare_int=False):
                 if wts is not None:
                     wts[i] = [1.0]
     ids, lens = _ragged_to_padded(nbrs, np.int32, -1)
+    if num_rows is not None:
+        ids = _wrap_negative(ids, lens, int(num_rows), check_upper)
     t_ids = torch.from_numpy(ids).to(device, non_blocking=True)
     t_len = torch.from_numpy(lens).to(device, non_blocking=True)
     if wts is None:

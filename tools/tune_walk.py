@@ -1,5 +1,5 @@
 """Times the walk kernel on config C2 in separate processes, one per variant.
-A variant is LEAF[:MINBLOCKS[:TABLE[:L2FETCH[:SMEMPAD[:W[:L]]]]]] -- LEAF in bucket / compact / wide (PB200_WALK_LEAF),
+A variant is LEAF[:MINBLOCKS[:TABLE[:L2FETCH[:SMEMPAD[:W[:L[:CARVEOUT%]]]]]]] -- LEAF in bucket / compact / wide (PB200_WALK_LEAF),
 MINBLOCKS = resident blocks per SM the lean bucket kernel is compiled for (PB200_WALK_MINBLOCKS),
 TABLE = visit-table version of the lean kernel (PB200_WALK_TABLE: 0 atomics, 1 / 2 match.any + plain
 stores with 256 / 512 slots), OLDVARIANT = PB200_WALK_VARIANT of the tree-index kernel.  Prints mean / min ms per launch and a
@@ -43,6 +43,7 @@ if not os.path.exists("/tmp/c2_graph.npz"):
     np.savez("/tmp/c2_graph.npz", ei=ei, w=w, N=M + U)
 variants = sys.argv[1:] or ["bucket:6:0", "bucket:6:0:32", "bucket:6:3:32", "bucket:6:4:32", "bucket:6:10:32", "bucket:6:13:32", "bucket:6:14:32", "bucket:8:14:32", "compact:::32"]
 for v in variants:
+    v, _, extra = v.partition("@")          # "...@KEY=VAL,KEY=VAL": extra environment for the child
     parts = v.split(":")
     env = dict(os.environ, PB200_WALK_LEAF=parts[0])
     if len(parts) > 1 and parts[1]:
@@ -57,5 +58,11 @@ for v in variants:
         env["TUNE_W"] = parts[5]
     if len(parts) > 6 and parts[6]:
         env["TUNE_L"] = parts[6]
+    if len(parts) > 7 and parts[7]:
+        env["PB200_WALK_CARVE"] = parts[7]
+    for kv in filter(None, extra.split(",")):
+        k_, _, v_ = kv.partition("=")
+        env[k_] = v_
+    v = v + ("@" + extra if extra else "")
     r = subprocess.run([sys.executable, "-c", CHILD % (ROOT, v)], env=env, capture_output=True, text=True, timeout=300)
     print((r.stdout.strip() or r.stderr.strip()[-600:]), flush=True)
