@@ -14,13 +14,20 @@ T=10 neighbours.  One step = 2 x [walk/count/top-T kernel over all items] + fuse
   cpu_baseline   the oracle port (C walk sampler on all host threads + numpy forward) on a
                  bounded sample, rank 0 at N=1
 
+  retrieval  BASELINE metric (2): all-item top-10 queries/s for exact / LSH / IVF search over C3-shaped
+             embeddings (bench_search.run_retrieval): set B (spread) at every N, set A (the embeddings
+             this run just computed from the reference checkpoint: collapsed) at N = 1
+
 N > 1 (torchrun): rows are split across ranks (strong scaling over the fixed catalogue); the
-pooling kernel reads neighbour rows of h from peer memory over NVLink, one one-element
-all-reduce per layer as a barrier; the per-rank step is replayed as a CUDA graph (sampling
-epochs advance on the device); time = max over ranks.
+pooling kernel reads neighbour rows of h from peer memory over NVLink, one flag barrier on peer
+memory per layer; the per-rank step is replayed as a CUDA graph (sampling epochs advance on the
+device; the e2e graph also holds the pinned-host upload, forked under the walks, and the download);
+time = max over ranks.  One untimed step is compared bitwise with the unsharded result on rank 0
+("sharded_equals_single"); retrieval runs query-sharded (and exact search item-sharded + merge).
 `--impl reference` times the CPU port alone (rank 0) and prints the same JSON shape.
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -48,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["fp32", "tf32", "auto"])
     ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the sharded step eagerly")
+    ap.add_argument("--no-retrieval", action="store_true", help="skip the retrieval (search) section")
     return ap.parse_args()
 
 
@@ -108,13 +116,26 @@ def build_inputs(workload):
 
 
 # ----------------------------------------------------------------------------- CPU port
+def model_weights(inp):
+    """C2 / C3 use the reference's shipped checkpoint (checkpoints/best_model.pt, committed as
+    tests/golden/checkpoint.npz by tests/golden/make_golden_r2.py); other shapes a seeded default init."""
+    from mre_b200.model.pinsage import PinSage
+    path = os.path.join(ROOT, "tests", "golden", "checkpoint.npz")
+    model = PinSage(inp["F"], inp["H"], inp["E"], inp["layers"])
+    if os.path.exists(path):
+        g = np.load(path)
+        if tuple(int(v) for v in g["dims"]) == (inp["F"], inp["H"], inp["E"], inp["layers"]):
+            model.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")})
+            return model, "reference checkpoint best_model.pt (tests/golden/checkpoint.npz)"
+    torch.manual_seed(0)
+    return PinSage(inp["F"], inp["H"], inp["E"], inp["layers"]), "seeded default init (torch.manual_seed(0))"
+
+
 def cpu_port_setup(inp):
     from oracle import oracle as O
     row_ptr, col, cum = O.c_csr_build(inp["ei"], inp["w"], inp["M"] + inp["U"], 1)
-    torch.manual_seed(0)
-    from mre_b200.model.pinsage import PinSage
-    sd = {k: v.detach().numpy() for k, v in
-          PinSage(inp["F"], inp["H"], inp["E"], inp["layers"]).state_dict().items()}
+    model, _src = model_weights(inp)
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
     return dict(O=O, csr=(row_ptr, col, cum), sd=sd, threads=O.c_oracle().orc_max_threads())
 
 
@@ -143,7 +164,8 @@ def run_cpu_port(inp, sample, steps, warmup):
     for s in range(steps):
         cpu_port_step(inp, cp, sample, warmup + s)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dict(value=sample / dt, unit=UNIT, cores=cp["threads"], kind="port",
+    return dict(value=sample / dt, unit=UNIT, cores=cp["threads"], kind="port", extrapolated=sample < inp["M"],
+                warmup_steps=warmup,
                 sample=f"{sample} of {inp['M']} start items per step (walks on the full graph, "
                        f"W=100 L=2 T=10, {inp['layers']} layers + forward on those rows); items/s "
                        "extrapolates linearly; C walk port on all host threads + numpy fp32 forward",
@@ -155,13 +177,15 @@ def main_reference(args):
     if rank != 0:
         return
     inp = build_inputs(args.workload)
-    r = run_cpu_port(inp, args.cpu_sample, args.steps, min(args.warmup, 1))
+    warm = min(args.warmup, 1)        # one warm-up step of ~0.3 s is enough for a CPU loop; reported as run
+    r = run_cpu_port(inp, args.cpu_sample, args.steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "warmup_requested": args.warmup,
+            "same_config": False, "extrapolated": r["extrapolated"],
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, inp, 1),
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -177,12 +201,51 @@ def workload_config(args, inp, n_gpus):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def walk_roofline(K, sampler, nodes, T, walk_ms, dev_ms, peaks_path):
+    """Roofline of the dominant kernel (walk / count / top-T) for THIS rank's start nodes: algorithmic bytes
+    (16 + 4 ceil(log2(deg+1)) + 4 per executed step, 4 + 12 T per start node) summed
+    exactly over the executed steps of one traced launch / mean CUDA-event duration of the launches."""
+    peaks = {}
+    try:
+        peaks = json.load(open(peaks_path))
+    except Exception:      # noqa: BLE001
+        pass
+    peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else \
+        (6650.0, "fallback (B200_PROFILING.md)")
+    _ids, _c, _w, _nv, trace = K.walk_topt(sampler.csr, nodes, 100, 2, T, 1234, 0, return_trace=True)
+    deg = (sampler.csr.row_ptr[1:] - sampler.csr.row_ptr[:-1])
+    cur = torch.cat([nodes.view(-1, 1, 1).expand(-1, 100, 1), trace[:, :, :-1]], dim=2).long()
+    executed = trace >= 0
+    d = deg[cur.clamp_min(0)].double()
+    per_step = 16 + 4 * torch.ceil(torch.log2(d + 1)) + 4
+    algo_bytes = float((per_step * executed).sum()) + nodes.numel() * (4 + 12 * T)
+    avg_ms = float(np.mean(walk_ms))
+    achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json")))
+        if nodes.numel() == tj.get("start_nodes"):
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+    except Exception:      # noqa: BLE001
+        pass
+    return {"kernel": "walk_bucket_batched_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src or "not measured in-run (needs ncu); see profiles/",
+            "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms,
+            "start_nodes_this_rank": int(nodes.numel()), "executed_steps": int(executed.sum()),
+            "share_of_step": sum(walk_ms) / dev_ms,
+            "limiter": "ncu (profiles/r2_walk_bucket_batched_ncu_details.txt): LSU data pipe 72 % of peak wavefronts "
+                       "(one wavefront per lane for the divergent 16 B meta and 32 B bucket loads + shared-memory atomics "
+                       "of the visit table), issue slots 65 %, DRAM 55 %: two dependent loads per step, latency / LSU bound"}
+
+
 def main_b200(args):
     import torch.distributed as dist
     import mre_b200  # noqa: F401
     from mre_b200 import _native as N, kernels as K, neighbor_lists as NL, sharding as SH
     from mre_b200.utils.random_walk import RandomWalkSampler
-    from mre_b200.model.pinsage import PinSage
+    from mre_b200.graphs import GraphedEmbeddings
+    import bench_search as BS
 
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -199,8 +262,8 @@ def main_b200(args):
                                 seed=1234, device=dev, num_nodes=M + inp["U"])
     torch.cuda.synchronize()
     csr_s = time.perf_counter() - t0
-    torch.manual_seed(0)
-    model = PinSage(inp["F"], inp["H"], inp["E"], layers).to(dev).eval()
+    model, weights_src = model_weights(inp)
+    model = model.to(dev).eval()
     model.precision = N.PRECISIONS[args.precision]
     lo, hi = SH.shard_range(M, rank, ws)
     x_host = inp["x"][lo:hi].contiguous().pin_memory()
@@ -214,13 +277,13 @@ def main_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graphed = None   # N > 1: the sharded step is launch bound -> one CUDA graph per rank (graphs.py)
+    graphed = graphed_e2e = None   # N > 1: the sharded step is launch bound -> one CUDA graph per rank (graphs.py)
 
     def step_device(walk_events=None):
         if ws > 1:
             if graphed is not None:
-                return graphed.replay()
-            return SH.get_embeddings_sharded(model, x_dev, sampler, M, T)
+                return graphed.replay(check=False)
+            return SH.get_embeddings_sharded(model, x_dev, sampler, M, T, check_barriers=False)
         batches = []
         for layer in range(layers):
             if walk_events is not None:
@@ -234,8 +297,13 @@ def main_b200(args):
 
     def step_e2e():
         if ws > 1:
-            emb = SH.get_embeddings_sharded(model, x_host, sampler, M, T)
+            if graphed_e2e is not None:          # upload (forked under the walks) + step + download: one graph
+                graphed_e2e.replay(check=False)
+                torch.cuda.current_stream(dev).synchronize()
+                return
+            emb = SH.get_embeddings_sharded(model, x_host, sampler, M, T, check_barriers=False)
             out_host.copy_(emb, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
         else:
             model.get_embeddings(x_host, sampler, T, out=out_host)
 
@@ -244,19 +312,37 @@ def main_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_device(); step_e2e()
     barrier()
+    if ws > 1:
+        SH.check_peer_barriers(force=True)
+
+    # ---- N > 1: one untimed sharded step vs the unsharded step on rank 0, bitwise ----
+    sharded_equals_single = None
+    if ws > 1:
+        e0 = sampler.epoch
+        mine = SH.get_embeddings_sharded(model, x_dev, sampler, M, T)
+        full = SH.all_gather_rows(mine, M)
+        if rank == 0:
+            sampler.epoch = e0
+            single = model.get_embeddings(inp["x"].to(dev), sampler, T)
+            sharded_equals_single = bool(torch.equal(full, single))
+            del single
+        sampler.epoch = e0 + layers
+        del full, mine
+        barrier()
+
     if ws > 1 and not args.no_graph:
-        from mre_b200.graphs import GraphedEmbeddings
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
             graphed = GraphedEmbeddings(model, x_dev, sampler, T, num_items=M)
+            graphed_e2e = GraphedEmbeddings(model, x_host, sampler, T, num_items=M, out=out_host)
         except Exception as e:          # noqa: BLE001 -- capture unsupported here: keep the eager step
             print(f"[bench] rank {rank}: CUDA-graph capture failed ({e}); eager launches", file=sys.stderr)
-            graphed, ok[0] = None, 0
+            graphed, graphed_e2e, ok[0] = None, None, 0
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks replay, or none
         if int(ok.item()) == 0:
-            graphed = None
+            graphed = graphed_e2e = None
         for _ in range(3):
-            step_device()
+            step_device(); step_e2e()
         barrier()
 
     # ---- timed: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
@@ -289,11 +375,36 @@ def main_b200(args):
     e2e_s = time.perf_counter() - t0
     clocks.active = False
     clocks.stop_flag = True
+    if ws > 1:
+        SH.check_peer_barriers(force=True)          # a barrier that gave up invalidates the run: raise
+
+    # N > 1: the walk kernel of this rank's shard, timed eagerly (the graph replays are timed as a whole)
+    if ws > 1:
+        for layer in range(4):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); sampler._sample(nodes, T, check=False); e1.record()
+            walk_events.append((e0, e1))
+        torch.cuda.synchronize()
+        walk_ms = [a.elapsed_time(b) for a, b in walk_events]
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = t.tolist()
+
+    # ---- retrieval (every rank takes part: query-sharded / item-sharded at N > 1) ----
+    retrieval = None
+    if not args.no_retrieval:
+        with contextlib.redirect_stdout(sys.stderr):
+            retrieval = BS.run_retrieval(dev, None, "B (1,024 clusters + 0.3 noise, SURVEY 8(d))", cpu=not args.no_cpu_baseline)
+            if ws == 1:
+                sampler.epoch = 0
+                emb_a = model.get_embeddings(x_dev, sampler, T)
+                ra = BS.run_retrieval(dev, emb_a, "A (this run's C2 embeddings from the reference checkpoint: collapsed, "
+                                      "SURVEY fact 9)", cpu=False, iters=1, methods=("exact_ip", "exact_l2", "lsh_exhaustive", "ivf"))
+                retrieval["set_A"] = {k: ra[k] for k in ("embedding_set", "methods")}
+                retrieval["set_A"]["mean_pairwise_cosine_sample"] = float((emb_a[:2048] @ emb_a[:2048].t()).mean())
     if rank != 0:
         if ws > 1:
             dist.destroy_process_group()
@@ -305,50 +416,34 @@ def main_b200(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "tf32 (fp32 accumulate; walks: u32/u64 integer)", "data": "synthetic",
             "config": dict(workload_config(args, inp, ws), l2="flushed between steps (256 MB "
-                           "write); CSR 0.6 GB exceeds the 126 MB L2",
-                           weights="seeded default init (torch.manual_seed(0))",
+                           "write); sampling index 0.6 GB exceeds the 126 MB L2",
+                           weights=weights_src,
                            step_launch="cuda graph replay per rank" if graphed is not None else "eager",
-                           exchange=os.environ.get("PB200_SHARD_EXCHANGE", "p2p") + " (neighbour rows of h)" if ws > 1 else "none",
+                           exchange=os.environ.get("PB200_SHARD_EXCHANGE", "p2p") + " (neighbour rows of h read from peer memory)" if ws > 1 else "none",
                            csr_build_s=round(csr_s, 3), graph_gen_s=round(inp["gen_s"], 1),
-                           csr_bytes=sampler.csr.nbytes(), walk_index_bytes=sampler.csr.index_nbytes(), wall_s_timed_region=round(wall_dev, 4)),
+                           csr_bytes=sampler.csr.nbytes(), walk_index_bytes=sampler.csr.index_nbytes(),
+                           walk_index="bucket" if sampler.csr.leaf_format == N.LEAF_BUCKET else "tree",
+                           wall_s_timed_region=round(wall_dev, 4)),
             "e2e": {"value": M * args.steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+                    "h2d_bytes_per_step": inp["x"].numel() * 4, "d2h_bytes_per_step": M * inp["E"] * 4,
+                    "ms_per_step": e2e_s / args.steps * 1e3,
+                    "path": "PinSage.get_embeddings(pinned x, sampler, T, out=pinned)" if ws == 1 else
+                            ("GraphedEmbeddings(pinned x shard, out=pinned).replay() per rank" if graphed_e2e is not None
+                             else "get_embeddings_sharded(pinned x shard) + D2H per rank")},
             "gpu_launches": launches, "clocks": clocks.summary()}
-
-    # ---- roofline of the dominant kernel (walk/count/top-T) ----
-    if ws == 1 and walk_ms:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        ids, _c, _w, _nv, trace = K.walk_topt(sampler.csr, nodes, 100, 2, T, 1234, 0, return_trace=True)
-        deg = (sampler.csr.row_ptr[1:] - sampler.csr.row_ptr[:-1])
-        cur = torch.cat([nodes.view(-1, 1, 1).expand(-1, 100, 1), trace[:, :, :-1]], dim=2).long()
-        executed = trace >= 0
-        d = deg[cur.clamp_min(0)].double()
-        per_step = 16 + 4 * torch.ceil(torch.log2(d + 1)) + 4
-        algo_bytes = float((per_step * executed).sum()) + M * (4 + 12 * T)
-        avg_ms = float(np.mean(walk_ms))
-        achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        line["roofline"] = {"kernel": "walk_topt_kernel", "bound": "hbm", "achieved": achieved,
-                            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                            "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes,
-                            "avg_launch_ms": avg_ms, "executed_steps": int(executed.sum()),
-                            "share_of_step": sum(walk_ms) / dev_ms,
-                            "limiter": "ncu (profiles/r1_walk_compact_leaf_ncu_details.txt): issue slots 64 % busy, "
-                                       "LSU data-pipe wavefronts 57 % of peak (divergent 32 B loads + shared-memory "
-                                       "atomics), DRAM ~30 %: the kernel is not HBM-bandwidth bound"}
+    if sharded_equals_single is not None:
+        line["sharded_equals_single"] = sharded_equals_single
+    if walk_ms:
+        line["roofline"] = walk_roofline(K, sampler, nodes, T, walk_ms, dev_ms if ws == 1 else float("nan"),
+                                         os.path.join(ROOT, "MEASURED_PEAKS.json"))
+        if ws > 1:
+            line["roofline"]["share_of_step"] = None
+            line["roofline"]["note"] = "rank 0's shard of the start nodes, kernel timed eagerly after the graph-replay region"
+    if retrieval is not None:
+        line["retrieval"] = retrieval
     if ws == 1 and not args.no_cpu_baseline:
         r = run_cpu_port(inp, args.cpu_sample, 3, 1)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")}
     print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()

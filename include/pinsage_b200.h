@@ -224,6 +224,11 @@ int pb200_peer_close(void* ptr);
  * *error_flag becomes 1 if a peer never arrives. */
 int pb200_peer_barrier(uint32_t* const* flag_ptrs_dev, uint32_t* seq_counter, int rank, int world,
                        uint32_t* error_flag, pb200_stream_t stream);
+/* Same with an explicit bound on the wait: max_spins polls of ~40 ns each (pb200_peer_barrier uses 2^27,
+ * about 5 s).  On time-out bit t of *error_flag is set for every peer t that never arrived; the caller
+ * must check the flag before trusting anything computed after the barrier (the Python mirror raises). */
+int pb200_peer_barrier_ex(uint32_t* const* flag_ptrs_dev, uint32_t* seq_counter, int rank, int world,
+                          uint32_t* error_flag, uint64_t max_spins, pb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * G1-G3  fused [gather -> importance sum -> concat -> dense -> epilogue]

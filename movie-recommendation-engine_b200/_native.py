@@ -60,6 +60,7 @@ SIGNATURES = {
     "pb200_peer_open": (c_int, [c_ptr, c_ptr]),
     "pb200_peer_close": (c_int, [c_ptr]),
     "pb200_peer_barrier": (c_int, [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
+    "pb200_peer_barrier_ex": (c_int, [c_ptr, c_ptr, c_int, c_int, c_ptr, c_u64, c_ptr]),
     "pb200_gather_dense": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int,
                                    c_int, c_int, c_ptr, c_ptr]),

@@ -154,7 +154,7 @@ extern "C" int pb200_pool_sharded(const float* const* shard_ptrs, int world, int
 // on time-out *error_flag is set and the kernel returns.
 namespace pb200 {
 __global__ void peer_barrier_kernel(uint32_t* const* __restrict__ flags, uint32_t* seq_counter, int rank,
-                                    int world, uint32_t* error_flag) {
+                                    int world, uint32_t* error_flag, unsigned long long max_spins) {
     const int t = threadIdx.x;
     const uint32_t seq = *seq_counter + 1u;
     __threadfence_system();                       // this rank's earlier writes before its flag
@@ -164,7 +164,7 @@ __global__ void peer_barrier_kernel(uint32_t* const* __restrict__ flags, uint32_
         volatile uint32_t* mine = flags[rank] + t;
         unsigned long long spins = 0;
         while ((int32_t)(*mine - seq) < 0) {
-            if (++spins > (1ull << 27)) { *error_flag = 1u; break; }
+            if (++spins > max_spins) { atomicOr(error_flag, 1u << (t & 31)); break; }   // bit t: peer t never arrived
             __nanosleep(40);
         }
     }
@@ -174,13 +174,18 @@ __global__ void peer_barrier_kernel(uint32_t* const* __restrict__ flags, uint32_
 }
 }  // namespace pb200
 
+extern "C" int pb200_peer_barrier_ex(uint32_t* const* flag_ptrs_dev, uint32_t* seq_counter, int rank, int world,
+                                     uint32_t* error_flag, uint64_t max_spins, pb200_stream_t stream) {
+    PB_REQUIRE(flag_ptrs_dev && seq_counter && error_flag && world >= 1 && world <= PB200_MAX_PEERS &&
+               rank >= 0 && rank < world && max_spins > 0, "peer_barrier: bad arguments");
+    pb200::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_ptrs_dev, seq_counter, rank, world,
+                                                                     error_flag, (unsigned long long)max_spins);
+    return check_launch("peer_barrier_kernel");
+}
+
 extern "C" int pb200_peer_barrier(uint32_t* const* flag_ptrs_dev, uint32_t* seq_counter, int rank, int world,
                                   uint32_t* error_flag, pb200_stream_t stream) {
-    PB_REQUIRE(flag_ptrs_dev && seq_counter && error_flag && world >= 1 && world <= PB200_MAX_PEERS &&
-               rank >= 0 && rank < world, "peer_barrier: bad arguments");
-    pb200::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_ptrs_dev, seq_counter, rank, world,
-                                                                     error_flag);
-    return check_launch("peer_barrier_kernel");
+    return pb200_peer_barrier_ex(flag_ptrs_dev, seq_counter, rank, world, error_flag, 1ull << 27, stream);
 }
 
 // ---- peer buffers: cudaMalloc'ed exchange buffers shared between the ranks of one box by CUDA IPC ----

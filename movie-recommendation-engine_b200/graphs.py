@@ -17,35 +17,64 @@ from . import sharding as SH
 
 
 class GraphedEmbeddings:
-    """graph = GraphedEmbeddings(model, x_dev, sampler, T[, num_items, group]); out = graph.replay().
+    """graph = GraphedEmbeddings(model, x, sampler, T[, num_items, group, out]); emb = graph.replay().
 
-    x_dev: device-resident features (this rank's rows when sharded).  `replay()` returns the
-    same output tensor every time (overwritten in place, stream ordered)."""
+    x: features (this rank's rows when sharded) -- device-resident, or a PINNED host tensor: the upload
+    then becomes a node of the graph on a forked stream, running under the walk kernels (which do not
+    need the features), and every replay re-reads the host buffer.  out: optional pinned host tensor
+    that receives the embeddings (a download node at the end of the graph).  `replay()` returns the
+    same tensor every time (overwritten in place, stream ordered)."""
 
-    def __init__(self, model, x_dev, sampler, num_neighbors=10, num_items=None, group=None, warmup=2):
+    def __init__(self, model, x, sampler, num_neighbors=10, num_items=None, group=None, warmup=2, out=None):
         dev = model._device()
         if dev.type != "cuda":
             raise N.NativeError("GraphedEmbeddings needs a CUDA device")
         rank, ws = SH.world(group)
+        self.ws = ws
         self.layers = model.num_layers
+        self.replays = 0
+        host_in = isinstance(x, torch.Tensor) and not x.is_cuda
+        if host_in and not x.is_pinned():
+            raise N.NativeError("GraphedEmbeddings: a host feature tensor must be pinned (the upload is a graph node)")
+        if out is not None and not out.is_cuda and not out.is_pinned():
+            raise N.NativeError("GraphedEmbeddings: a host output tensor must be pinned")
         # the graph bakes in addresses: keep every captured input alive for the graph's lifetime
-        self.model, self.x_dev, self.sampler = model, x_dev, sampler
+        self.model, self.x_src, self.sampler, self.out_host = model, x, sampler, out
+        self.x_dev = torch.empty(x.shape, dtype=torch.float32, device=dev) if host_in else x
         self.base = int(sampler.epoch)
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        n_items = x_dev.size(0) if num_items is None else int(num_items)
+        n_items = x.size(0) if num_items is None else int(num_items)
         lo, hi = SH.shard_range(n_items, rank, ws)
         nodes = self.nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+        side_up = torch.cuda.Stream(dev) if host_in else None
 
-        def step():
-            if ws > 1:
-                return SH.get_embeddings_sharded(model, x_dev, sampler, n_items, num_neighbors, group,
-                                                 epoch_base=self.base, epoch_dev=self.epoch_dev)
+        def sample():
             batches = []
             for layer in range(self.layers):
                 ids, _c, w, nv = sampler._sample(nodes, num_neighbors, epoch=self.base + layer, check=False,
                                                  epoch_dev=self.epoch_dev)
                 batches.append(NL.from_walk(ids, w, nv))
-            return model.forward(x_dev, None, batches, None)
+            return batches
+
+        def step():
+            cur = torch.cuda.current_stream(dev)
+            if host_in:                                  # fork: upload under the walks
+                side_up.wait_stream(cur)
+                with torch.cuda.stream(side_up):
+                    self.x_dev.copy_(x, non_blocking=True)
+            if ws > 1:
+                emb = SH.get_embeddings_sharded(model, self.x_dev, sampler, n_items, num_neighbors, group,
+                                                epoch_base=self.base, epoch_dev=self.epoch_dev,
+                                                check_barriers=False,
+                                                before_forward=(lambda: cur.wait_stream(side_up)) if host_in else None)
+            else:
+                batches = sample()
+                if host_in:
+                    cur.wait_stream(side_up)
+                emb = model.forward(self.x_dev, None, batches, None)
+            if out is not None:
+                out.copy_(emb, non_blocking=True)
+            return emb
 
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
@@ -55,6 +84,8 @@ class GraphedEmbeddings:
                 step()
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        if ws > 1:
+            SH.check_peer_barriers()
         self.epoch_dev.zero_()
         self.graph = torch.cuda.CUDAGraph()
         l0 = N.launch_count()
@@ -63,6 +94,14 @@ class GraphedEmbeddings:
             K.u32_add(self.epoch_dev, self.layers)
         self.launches_per_replay = N.launch_count() - l0
 
-    def replay(self):
+    def replay(self, check=True):
+        """One step.  check (sharded graphs): read the peer barriers' time-out flag afterwards (a stream
+        sync) and raise if a peer never arrived; a pipelined loop passes False and calls
+        sharding.check_peer_barriers(force=True) before it trusts the results."""
         self.graph.replay()
-        return self.out
+        self.replays += 1
+        # eager sampling calls made after replays continue the epoch sequence instead of reusing it
+        self.sampler.epoch = max(self.sampler.epoch, self.base + self.replays * self.layers)
+        if check and self.ws > 1:
+            SH.check_peer_barriers(force=True)
+        return self.out if self.out_host is None else self.out_host

@@ -275,8 +275,9 @@ def tf32_weight(w):
 
 
 def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N.POOL_PINSAGE,
-                 flags=0, precision=N.PREC_FP32, ln_gamma=None, ln_beta=None, n=None):
-    """out = epi([a1 | a2-or-pooled] @ w.T + bias).  lists = (ids, weights, list_len, weight_len)."""
+                 flags=0, precision=N.PREC_FP32, ln_gamma=None, ln_beta=None, n=None, out=None):
+    """out = epi([a1 | a2-or-pooled] @ w.T + bias).  lists = (ids, weights, list_len, weight_len).
+    out: optional contiguous float32 [n, n_out] device buffer to write into (e.g. a peer-memory shard)."""
     dev = N.device_of(w)
     if precision != N.PREC_FP32:
         w = tf32_weight(w)
@@ -296,7 +297,10 @@ def gather_dense(a1, w, bias=None, a2=None, pool_x=None, lists=None, pool_mode=N
     if pool_x is not None:
         ids, wts, ll, wl = lists
         T = ids.size(1)
-    out = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (n, n_out) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 [{n}, {n_out}] tensor")
     check(lib().pb200_gather_dense(ptr(a1), k1, ptr(a2), k2, ptr(pool_x),
                                    0 if pool_x is None else pool_x.size(0), ptr(ids), ptr(wts),
                                    ptr(ll), ptr(wl), T, pool_mode, ptr(w), ptr(bias),

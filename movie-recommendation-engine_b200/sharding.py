@@ -170,11 +170,30 @@ class PeerBuffers:
         after it starts on any rank: one small kernel on peer-memory flags (pb200_peer_barrier), so
         a step containing it can be captured in a CUDA graph."""
         from . import _native as N
-        N.check(N.lib().pb200_peer_barrier(N.ptr(self._flag_ptrs), N.ptr(self._seq[0:1]), self.rank, self.ws,
-                                           N.ptr(self._seq[1:2]), N.stream_ptr(self.dev)), "peer_barrier")
+        N.check(N.lib().pb200_peer_barrier_ex(N.ptr(self._flag_ptrs), N.ptr(self._seq[0:1]), self.rank, self.ws,
+                                              N.ptr(self._seq[1:2]), self.max_spins, N.stream_ptr(self.dev)),
+                "peer_barrier")
+        self._unchecked = True
+
+    max_spins = 1 << 27            # ~5 s of 40 ns polls before a barrier gives up
 
     def timed_out(self):
-        return bool(self._seq[1].item())
+        """Bit mask of the peers a barrier gave up waiting for since the last check (device sync)."""
+        return int(self._seq[1].item()) & 0xFFFFFFFF
+
+    def check(self):
+        """Raises if any barrier since the last check timed out: what was pooled after it may have read
+        rows a peer had not written yet.  Synchronises the stream; clears the flag."""
+        from . import _native as N
+        if not getattr(self, "_unchecked", False):
+            return
+        missing = self.timed_out()
+        self._unchecked = False
+        if missing:
+            self._seq[1].zero_()
+            peers = [r for r in range(self.ws) if missing >> r & 1]
+            raise N.NativeError(f"rank {self.rank}: peer barrier timed out waiting for rank(s) {peers}; the "
+                                "embeddings of this step are not valid")
 
     def close(self):
         torch.cuda.synchronize(self.dev)
@@ -200,6 +219,16 @@ def peer_buffers(count, shard_rows, width, dev, group=None):
     return pb if pb.ok else None
 
 
+def check_peer_barriers(force=False):
+    """Raises NativeError if any peer barrier issued since the last check timed out (see PeerBuffers.check).
+    force: also read the flag when no barrier was issued from Python (CUDA-graph replays issue them)."""
+    for pb in _PEER_CACHE.values():
+        if pb.ok:
+            if force:
+                pb._unchecked = True
+            pb.check()
+
+
 def release_peer_buffers():
     for pb in _PEER_CACHE.values():
         if pb.ok:
@@ -218,51 +247,64 @@ def _use_peer_exchange(model, dev, ws):
 
 
 def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None,
-                           epoch_base=None, epoch_dev=None):
+                           epoch_base=None, epoch_dev=None, check_barriers=True, before_forward=None):
     """PinSage.get_embeddings with rows split across ranks.  x_local: this rank's rows of the
     feature matrix (shard_range layout).  Returns this rank's rows of the embeddings.
     epoch_base / epoch_dev: fixed host epoch + device-side counter (CUDA-graph capture, see
-    graphs.GraphedEmbeddings); by default the sampler's own epoch counter advances."""
+    graphs.GraphedEmbeddings); by default the sampler's own epoch counter advances.
+    check_barriers: read the peer barriers' time-out flag after the step (one stream sync) and raise
+    if a peer never arrived; pass False inside a CUDA-graph capture or a pipelined loop and call
+    sharding.check_peer_barriers() before using the results.
+    before_forward: optional callable run after the walk kernels are queued and before the features are
+    first read (e.g. a stream wait on an upload that runs under the walks)."""
     from . import _native as N
     from . import kernels as K
     from . import neighbor_lists as NL
     rank, ws = world(group)
     lo, hi = shard_range(num_items, rank, ws)
     dev = model._device()
-    xd = N.dev_tensor(x_local, torch.float32, dev)
     nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
     batches = []
     for layer in range(model.num_layers):                   # same epochs on every rank
         ids, _c, w, nv = sampler._sample(nodes, num_neighbors, check=False, epoch_dev=epoch_dev,
                                          epoch=None if epoch_base is None else epoch_base + layer)
         batches.append(NL.from_walk(ids, w, nv))
+    if before_forward is not None:
+        before_forward()
+    xd = N.dev_tensor(x_local, torch.float32, dev)
     P = lambda lin: (lin.weight, lin.bias)     # Parameter objects: identity keys the TF32 weight cache
     RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward
     PRE = 0 if model.precision == N.PREC_FP32 else N.IN_A1_TF32
-    h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
     pb = None
     if _use_peer_exchange(model, dev, ws):
         srows = shard_size(num_items, ws)
-        pb = peer_buffers(model.num_layers, srows, h_loc.size(1), dev, group)
+        pb = peer_buffers(model.num_layers, srows, model.input_proj.out_features, dev, group)
     if pb is not None:
-        # neighbour rows are read from their owners' memory; no all-gather
+        # neighbour rows are read from their owners' memory; no all-gather.  Every layer's output is
+        # written by its GEMM straight into this rank's peer-visible shard of the next layer's input.
+        rows = hi - lo
+        h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision,
+                               out=pb.local(0)[:rows])
         for i in range(model.num_layers):
-            mine = pb.local(i)[:hi - lo]
-            mine.copy_(h_loc)
             pb.barrier()                                        # every rank's h^(i) is in place
             wf, bf = model._folded_layer(i)
             ids, wts, ll, wl = batches[i].as_args()
             h_neigh = K.pool_sharded(pb.ptr_array(i), ws, srows, num_items, h_loc.size(1), ids, wts, ll, wl,
                                      N.POOL_PINSAGE | N.POOL_ROUND_TF32, dev)
-            h_loc = K.gather_dense(mine, wf, bf, a2=h_neigh,
+            h_loc = K.gather_dense(h_loc, wf, bf, a2=h_neigh,
                                    flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
-                                   precision=model.precision)
+                                   precision=model.precision,
+                                   out=pb.local(i + 1)[:rows] if i + 1 < model.num_layers else None)
         # Buffer i is rewritten by the next call only after the barrier of layer i+1 (which every
         # rank reaches after its pooling of layer i); a single layer has no such barrier.
         if model.num_layers == 1:
             pb.barrier()
-        return K.gather_dense(h_loc, *P(model.output_proj), flags=N.EPI_L2NORM | PRE,
-                              precision=model.precision)
+        emb = K.gather_dense(h_loc, *P(model.output_proj), flags=N.EPI_L2NORM | PRE,
+                             precision=model.precision)
+        if check_barriers:
+            pb.check()
+        return emb
+    h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
     for i in range(model.num_layers):
         h_full = all_gather_rows(h_loc, num_items, group)   # the one exchange per layer
         wf, bf = model._folded_layer(i)

@@ -229,3 +229,57 @@ def test_graphed_embeddings_replays_equal_eager_calls(dev):
         sampler.epoch = 40 + 2 * k
         want = model.get_embeddings(x, sampler, 10)
         assert torch.equal(got, want)
+
+
+def test_pooling_negative_ids_follow_python_indexing_like_the_reference(dev):
+    """negative neighbour ids index from the end in every reference class (x[list]); ids below
+    -M raise IndexError.  Golden: tests/golden/pooling_negative.npz from the unmodified reference."""
+    import json
+    from mre_b200.model.pinsage import ImportancePooling
+    from mre_b200.model.layers import ImportancePoolingLayer, WeightedMeanPoolingLayer, MaxPoolingLayer
+    from mre_b200.model.aggregators import WeightedAggregator, MeanAggregator, ImportanceAggregator
+    g = Hh.load("pooling_negative.npz")
+    meta = json.loads(str(g["lists"]))
+    x = torch.from_numpy(g["x"]).to(dev)
+    M = x.size(0)
+    nbrs, wts, nb_ok, wt_ok = meta["nbrs"], meta["wts"], meta["nb_ok"], meta["wt_ok"]
+    assert any(v < 0 for l in nbrs for v in l)
+    tol = dict(rtol=1e-5, atol=1e-6)
+    chk = lambda got, key: np.testing.assert_allclose(got.cpu().numpy(), g[key], **tol)
+    chk(ImportancePooling()(x, nbrs, wts), "pinsage")
+    chk(ImportancePoolingLayer()(x, nbrs, wts), "layers_importance")
+    chk(WeightedMeanPoolingLayer()(x, nbrs, wts), "layers_wmean")
+    chk(MaxPoolingLayer()(x, nbrs), "layers_max")
+    chk(WeightedAggregator()(x, nb_ok, wt_ok), "agg_weighted")
+    chk(MeanAggregator()(x, nb_ok), "agg_mean")
+    ia = ImportanceAggregator(x.size(1), 8).to(dev)
+    with torch.no_grad():
+        ia.transform.weight.copy_(torch.from_numpy(g["ia_W"])); ia.transform.bias.copy_(torch.from_numpy(g["ia_b"]))
+        ia.norm.weight.copy_(torch.from_numpy(g["ia_gamma"])); ia.norm.bias.copy_(torch.from_numpy(g["ia_beta"]))
+    np.testing.assert_allclose(ia(x, nb_ok, wt_ok).cpu().numpy(), g["agg_importance"], rtol=1e-4, atol=1e-5)
+    assert set(meta["raises"].values()) == {"IndexError"}          # what the reference does below -M ...
+    bad, bw = [[1, -M - 3]], [[0.5, 0.5]]
+    for call in (lambda: ImportancePooling()(x, bad, bw), lambda: ImportancePoolingLayer()(x, bad, bw),
+                 lambda: WeightedMeanPoolingLayer()(x, bad, bw), lambda: MaxPoolingLayer()(x, bad),
+                 lambda: WeightedAggregator()(x, bad, bw), lambda: MeanAggregator()(x, bad), lambda: ia(x, bad, bw)):
+        with pytest.raises(IndexError):                             # ... and what the drop-ins do
+            call()
+
+
+def test_reference_checkpoint_loads_and_matches_reference_outputs(dev):
+    """checkpoints/best_model.pt (committed as a state_dict fixture): loads by the reference's key names;
+    MLP branch and importance branch equal the unmodified reference's outputs (fp32 path <= 1e-3, and the
+    TF32 tensor-core path within the same bar)."""
+    import json
+    from mre_b200 import _native as N
+    g = Hh.load("checkpoint.npz")
+    model, layers = _load_model(g, dev)
+    assert tuple(int(v) for v in g["dims"]) == (128, 256, 128, 2)
+    x = torch.from_numpy(g["x"]).to(dev)
+    meta = json.loads(str(g["lists"]))
+    nb = [meta[f"nb{i}"] for i in range(layers)]
+    wt = [meta[f"wt{i}"] for i in range(layers)]
+    for prec in (N.PREC_FP32, N.PREC_AUTO):
+        model.precision = prec
+        assert Hh.rel_row_err(model(x).cpu().numpy(), g["emb_mlp"]) < TOL
+        assert Hh.rel_row_err(model(x, None, nb, wt).cpu().numpy(), g["emb_imp"]) < TOL

@@ -363,3 +363,65 @@ def test_indexes_leave_the_tensor_core_path_on_near_tied_data(K):
     a1 = ivf.search(x[:600], 10)
     a2 = ivf.search(x[:600], 10)
     np.testing.assert_array_equal(a1[1], a2[1]); np.testing.assert_array_equal(a1[0], a2[0])
+
+
+# ---- tensor-core kernels against the ORACLE directly (the tcgen05 paths were only compared
+# with this repo's own fp32 / popcount / list-scan kernels; the chain to the oracle was transitive) ----
+@pytest.mark.parametrize("nq,nx,d,k,metric", [(300, 5000, 128, 10, "ip"), (512, 4096, 64, 10, "l2"),
+                                              (257, 3001, 256, 16, "ip"), (1000, 2500, 32, 24, "l2")])
+def test_exact_topk_tensor_core_vs_oracle(K, nq, nx, d, k, metric):
+    from mre_b200 import _native as N
+    import mre_b200.synthetic as S
+    x = S.spread_embeddings(nx, d, seed=11, clusters=64, noise=0.3).numpy()
+    q = S.spread_embeddings(nq, d, seed=12, clusters=64, noise=0.3).numpy()
+    st = {}
+    s, i = K.topk(torch.from_numpy(q), torch.from_numpy(x), k, N.METRIC_IP if metric == "ip" else N.METRIC_L2,
+                  precision="tf32", stats=st)
+    assert st["path"] == "tf32"
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    rs, ri = (O.exact_ip if metric == "ip" else O.exact_l2)(x, q, k)
+    np.testing.assert_allclose(s, rs, atol=2e-5)                           # by score
+    assert (i == ri).mean() > 0.98                                         # ids, up to fp32 near-ties
+    for a, b in zip(i.tolist(), ri.tolist()):                              # top-k SETS match (north-star bar)
+        assert len(set(a) & set(b)) >= k - 1
+
+
+@pytest.mark.parametrize("nq,nx,nbits,k", [(300, 5000, 256, 10), (256, 2049, 128, 32), (700, 3000, 512, 10)])
+def test_hamming_topk_tensor_core_vs_oracle(K, nq, nx, nbits, k):
+    rng = np.random.Generator(np.random.PCG64(nbits + nq))
+    cx = rng.integers(0, 256, size=(nx, nbits // 8), dtype=np.uint8)
+    cq = np.concatenate([cx[:nq // 2], rng.integers(0, 256, size=(nq - nq // 2, nbits // 8), dtype=np.uint8)])
+    dist, ids = K.hamming_topk(torch.from_numpy(cq).cuda(), torch.from_numpy(cx).cuda(), k, precision="tc")
+    rd, ri = O.lsh_search_exhaustive(cx, cq, k)
+    np.testing.assert_array_equal(dist.cpu().numpy(), rd)                  # Hamming ints: exact
+    np.testing.assert_array_equal(ids.cpu().numpy(), ri)                   # (distance, id) total order
+
+
+@pytest.mark.parametrize("n,d,nbits", [(3000, 128, 256), (513, 64, 128)])
+def test_lsh_encode_tensor_core_vs_oracle(K, n, d, nbits):
+    x = _data(n, d, 31)
+    A = O.lsh_rotation(d, nbits)
+    ref_codes, y = O.lsh_encode(x, A)
+    codes = K.lsh_encode(torch.from_numpy(x), torch.from_numpy(A), precision="tc").cpu().numpy()
+    diff_bits = np.unpackbits(codes ^ ref_codes, axis=1, bitorder="little").astype(bool)
+    assert diff_bits.mean() < 1e-4 and np.all(np.abs(y[diff_bits]) < 1e-6)  # north-star bar for the codes
+
+
+def test_ivf_search_tensor_core_vs_oracle(K):
+    from mre_b200 import _native as N
+    import mre_b200.synthetic as S
+    n, d, nlist, nq, k = 20000, 64, 100, 600, 10
+    x = S.spread_embeddings(n, d, seed=4, clusters=200, noise=0.25).numpy()
+    cent = O.kmeans(x, nlist, niter=4)
+    xt, ct = torch.from_numpy(x).cuda(), torch.from_numpy(cent).cuda()
+    _, a = K.topk(xt, ct, 1, N.METRIC_L2)
+    assign = a.view(-1).contiguous()
+    lists = K.ivf_build(xt, assign, nlist)
+    lay = K.ivf_tc_layout(*lists, nlist)
+    q = xt[:nq].contiguous()
+    _, probes = K.topk(q, ct, 20, N.METRIC_L2)
+    assert K.ivf_search_tc_supported(nq, lay[0].size(0), d, k, nlist)
+    dist, ids = K.ivf_search_tc(q, probes, *lists, lay, nlist, k)
+    rd, ri = O.ivf_search(x, cent, assign.cpu().numpy(), x[:nq], k, 20)
+    np.testing.assert_allclose(dist.cpu().numpy(), rd, atol=2e-5)
+    assert (ids.cpu().numpy() == ri).mean() > 0.98

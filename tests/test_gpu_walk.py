@@ -270,3 +270,36 @@ def test_bucket_index_fallbacks(K):
     with pytest.raises(NV.NativeError):
         K.csr_build(torch.from_numpy(ei), torch.from_numpy(w0), num_nodes=400, index="bucket")
     assert K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=400).leaf_format == NV.LEAF_BUCKET
+
+
+def test_walk_distribution_matches_the_unpatched_reference_sampler(K):
+    """the Philox kernel against the UNPATCHED reference (global MT19937, np.random.choice):
+    visit frequencies of step 1 and step 2 over 20,000 walks per start node.  Two independent samples of
+    the same multinomial: chi-square homogeneity statistic within 4.5 sigma of its mean (df) and total
+    variation distance below the sampling-noise bound."""
+    g = Hh.load("walk_distribution.npz")
+    ei, w, starts, n_walks = g["edge_index"], g["edge_weights"], g["starts"], int(g["n_walks"])
+    ref = g["hist"].astype(np.float64)                                  # [starts, 2, N]
+    N = ref.shape[2]
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=N)
+    got = np.zeros_like(ref)
+    per_launch = 100
+    for e in range(n_walks // per_launch):                             # 200 epochs x 100 walks
+        *_x, trace = K.walk_topt(csr, torch.from_numpy(starts), per_launch, 2, 1, 777, e, return_trace=True)
+        tr = trace.cpu().numpy()                                        # [starts, 100, 2]
+        for si in range(len(starts)):
+            for step in range(2):
+                v = tr[si, :, step]
+                got[si, step] += np.bincount(v[v >= 0], minlength=N)
+    for si in range(len(starts)):
+        for step in range(2):
+            a, b = ref[si, step], got[si, step]
+            assert a.sum() == n_walks and b.sum() == n_walks
+            keep = (a + b) >= 10                                        # pool the rare cells
+            a2 = np.append(a[keep], a[~keep].sum()); b2 = np.append(b[keep], b[~keep].sum())
+            nz = (a2 + b2) > 0
+            chi2 = float((((a2 - b2) ** 2)[nz] / (a2 + b2)[nz]).sum())  # two-sample chi-square, equal totals
+            df = int(nz.sum()) - 1
+            assert abs(chi2 - df) < 4.5 * np.sqrt(2 * df) + 5, (si, step, chi2, df)
+            tv = 0.5 * np.abs(a / n_walks - b / n_walks).sum()
+            assert tv < 2.5 * np.sqrt(df / (2 * np.pi * n_walks)) + 0.01, (si, step, tv)
