@@ -201,7 +201,7 @@ def workload_config(args, inp, n_gpus):
 
 
 # ----------------------------------------------------------------------------- B200 arm
-def walk_roofline(K, sampler, nodes, T, walk_ms, dev_ms, peaks_path):
+def walk_roofline(K, sampler, nodes, T, layers, walk_ms, dev_ms, peaks_path):
     """Roofline of the dominant kernel (walk / count / top-T) for THIS rank's start nodes: algorithmic bytes
     (16 + 4 ceil(log2(deg+1)) + 4 per executed step, 4 + 12 T per start node) summed
     exactly over the executed steps of one traced launch / mean CUDA-event duration of the launches."""
@@ -212,19 +212,20 @@ def walk_roofline(K, sampler, nodes, T, walk_ms, dev_ms, peaks_path):
         pass
     peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else \
         (6650.0, "fallback (B200_PROFILING.md)")
-    _ids, _c, _w, _nv, trace = K.walk_topt(sampler.csr, nodes, 100, 2, T, 1234, 0, return_trace=True)
+    _ids, _c, _w, _nv, trace = K.walk_topt(sampler.csr, nodes, 100, 2, T, 1234, 0, return_trace=True,
+                                           num_epochs=layers)          # [layers, n, W, L]: what one launch executes
     deg = (sampler.csr.row_ptr[1:] - sampler.csr.row_ptr[:-1])
-    cur = torch.cat([nodes.view(-1, 1, 1).expand(-1, 100, 1), trace[:, :, :-1]], dim=2).long()
+    cur = torch.cat([nodes.view(1, -1, 1, 1).expand(layers, -1, 100, 1), trace[:, :, :, :-1]], dim=3).long()
     executed = trace >= 0
     d = deg[cur.clamp_min(0)].double()
     per_step = 16 + 4 * torch.ceil(torch.log2(d + 1)) + 4
-    algo_bytes = float((per_step * executed).sum()) + nodes.numel() * (4 + 12 * T)
+    algo_bytes = float((per_step * executed).sum()) + layers * nodes.numel() * (4 + 12 * T)
     avg_ms = float(np.mean(walk_ms))
     achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json")))
-        if nodes.numel() == tj.get("start_nodes"):
+        if nodes.numel() == tj.get("start_nodes") and layers == tj.get("samples_per_launch", 1):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
     except Exception:      # noqa: BLE001
         pass
@@ -232,7 +233,9 @@ def walk_roofline(K, sampler, nodes, T, walk_ms, dev_ms, peaks_path):
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_src or "not measured in-run (needs ncu); see profiles/",
             "peak_source": which, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms,
-            "start_nodes_this_rank": int(nodes.numel()), "executed_steps": int(executed.sum()),
+            "start_nodes_this_rank": int(nodes.numel()), "samples_per_launch": layers,
+            "launch": f"one launch = {layers} independent samples (one per conv layer) of every start node",
+            "executed_steps": int(executed.sum()),
             "share_of_step": sum(walk_ms) / dev_ms,
             "limiter": "ncu (profiles/r2_walk_bucket_batched_ncu_details.txt): LSU data pipe 72 % of peak wavefronts "
                        "(one wavefront per lane for the divergent 16 B meta and 32 B bucket loads + shared-memory atomics "
@@ -284,15 +287,12 @@ def main_b200(args):
             if graphed is not None:
                 return graphed.replay(check=False)
             return SH.get_embeddings_sharded(model, x_dev, sampler, M, T, check_barriers=False)
-        batches = []
-        for layer in range(layers):
-            if walk_events is not None:
-                e0 = torch.cuda.Event(enable_timing=True); e0.record()
-            ids, _c, w, nv = sampler._sample(nodes, T, check=False)
-            if walk_events is not None:
-                e1 = torch.cuda.Event(enable_timing=True); e1.record()
-                walk_events.append((e0, e1))
-            batches.append(NL.from_walk(ids, w, nv))
+        if walk_events is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        batches = sampler.sample_layers(nodes, T, layers)           # ONE launch: both layers' samples
+        if walk_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record()
+            walk_events.append((e0, e1))
         return model.forward(x_dev, None, batches, None)
 
     def step_e2e():
@@ -380,10 +380,10 @@ def main_b200(args):
 
     # N > 1: the walk kernel of this rank's shard, timed eagerly (the graph replays are timed as a whole)
     if ws > 1:
-        for layer in range(4):
+        for _ in range(4):
             flush.zero_()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); sampler._sample(nodes, T, check=False); e1.record()
+            e0.record(); sampler.sample_layers(nodes, T, layers); e1.record()
             walk_events.append((e0, e1))
         torch.cuda.synchronize()
         walk_ms = [a.elapsed_time(b) for a, b in walk_events]
@@ -434,7 +434,7 @@ def main_b200(args):
     if sharded_equals_single is not None:
         line["sharded_equals_single"] = sharded_equals_single
     if walk_ms:
-        line["roofline"] = walk_roofline(K, sampler, nodes, T, walk_ms, dev_ms if ws == 1 else float("nan"),
+        line["roofline"] = walk_roofline(K, sampler, nodes, T, layers, walk_ms, dev_ms if ws == 1 else float("nan"),
                                          os.path.join(ROOT, "MEASURED_PEAKS.json"))
         if ws > 1:
             line["roofline"]["share_of_step"] = None

@@ -160,6 +160,15 @@ int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* idx, const 
                                uint32_t epoch, const uint32_t* epoch_dev, int32_t* out_ids,
                                int32_t* out_counts, float* out_weights, int32_t* out_nvalid,
                                int32_t* trace_out, pb200_stream_t stream);
+/* num_epochs independent samples per start node (epochs epoch .. epoch + num_epochs - 1, as PinSage.get_embeddings
+ * draws one sample per layer, model/pinsage.py:271-275) -- ONE launch over (epoch, start) pairs on the bucket
+ * index, a loop of launches otherwise.  Outputs carry a leading epoch dimension: out_ids / out_counts /
+ * out_weights [num_epochs, n, T], out_nvalid [num_epochs, n], trace_out [num_epochs, n, W, L]. */
+int pb200_walk_topt_indexed_multi(const uint32_t* meta, const uint32_t* idx, const uint32_t* leaf, int leaf_format,
+                                  int64_t num_nodes, const int32_t* starts, int64_t n, int num_walks,
+                                  int walk_length, int num_neighbors, uint64_t seed, uint32_t epoch,
+                                  const uint32_t* epoch_dev, int num_epochs, int32_t* out_ids, int32_t* out_counts,
+                                  float* out_weights, int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream);
 int pb200_u32_add(uint32_t* counter, uint32_t delta, pb200_stream_t stream);
 
 /* Counting stage alone, given traces (parity "given the same walk traces"):

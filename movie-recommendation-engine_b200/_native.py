@@ -48,6 +48,9 @@ SIGNATURES = {
     "pb200_walk_topt_indexed_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_int,
                                            c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                            c_ptr]),
+    "pb200_walk_topt_indexed_multi": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_int,
+                                              c_int, c_u64, c_u32, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                              c_ptr]),
     "pb200_u32_add": (c_int, [c_ptr, c_u32, c_ptr]),
     "pb200_count_topt": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pb200_pool": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int,

@@ -34,7 +34,8 @@ struct WalkParams {
     const uint32_t* __restrict__ leaf;
     int leaf_compact;                       // PB200_LEAF_COMPACT: 32-byte leaf blocks
     int leaf_format;
-    int64_t n;
+    int64_t n;              // work items = start nodes x epochs
+    int64_t n_starts;       // start nodes per epoch (fast kernels: item s = (epoch s / n_starts, start s % n_starts))
     int64_t num_nodes;
     int W, L, T;
     int slots, slot_shift;  // hash table size (power of two) and 32 - log2(slots)
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const Walk
     const int warp = threadIdx.x >> 5;
     int32_t* keys = smem + warp * 768;                  // [keys | cnt | first] x 256 slots
     const int L = kL ? kL : p.L;
-    const uint32_t epoch = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
+    const uint32_t epoch0 = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
     for (int64_t s = (int64_t)blockIdx.x * 8 + warp; s < p.n; s += (int64_t)gridDim.x * 8) {
         {   // clear: lane owns 8 consecutive slots of each array (two 128-bit stores each)
             int4* k4 = reinterpret_cast<int4*>(keys) + lane * 2;
@@ -688,7 +689,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_kernel(const Walk
             k4[0] = e; k4[1] = e; k4[64] = z; k4[65] = z; k4[128] = e; k4[129] = e;
         }
         __syncwarp();
-        const int start = __ldg(p.starts + s);
+        const int64_t e_idx = s / p.n_starts;                   // several sampling epochs in one launch
+        const int start = __ldg(p.starts + (s - e_idx * p.n_starts));
+        const uint32_t epoch = epoch0 + (uint32_t)e_idx;
         for (int base = 0; base < p.W; base += 32) {
             const int walk = base + lane;
             bool alive = walk < p.W;
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_batched_kernel(co
     const int warp = threadIdx.x >> 5;
     int32_t* keys = smem + warp * 768;                  // [keys | cnt | first] x 256 slots
     const int L = kL ? kL : p.L;
-    const uint32_t epoch = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
+    const uint32_t epoch0 = p.epoch + (p.epoch_dev ? __ldg(p.epoch_dev) : 0u);
     for (int64_t s = (int64_t)blockIdx.x * 8 + warp; s < p.n; s += (int64_t)gridDim.x * 8) {
         {
             int4* k4 = reinterpret_cast<int4*>(keys) + lane * 2;
@@ -734,7 +737,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_batched_kernel(co
             k4[0] = e; k4[1] = e; k4[64] = z; k4[65] = z; k4[128] = e; k4[129] = e;
         }
         __syncwarp();
-        const int start = __ldg(p.starts + s);
+        const int64_t e_idx = s / p.n_starts;                   // several sampling epochs in one launch
+        const int start = __ldg(p.starts + (s - e_idx * p.n_starts));
+        const uint32_t epoch = epoch0 + (uint32_t)e_idx;
         for (int base = 0; base < p.W; base += 32 * kB) {
             int cur[kB]; bool alive[kB]; Philox4 r[kB];
 #pragma unroll
@@ -937,7 +942,7 @@ extern "C" int pb200_walk_topt(const int64_t* row_ptr, const int32_t* col, const
                out_nvalid, "walk_topt: null pointer");
     WalkParams p{};
     p.row_ptr = row_ptr; p.col = col; p.cum = cum; p.starts = starts; p.trace_in = nullptr;
-    p.n = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
+    p.n = n; p.n_starts = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.epoch = epoch;
     p.out_ids = out_ids; p.out_counts = out_counts; p.out_w = out_weights;
     p.out_nvalid = out_nvalid; p.trace_out = trace_out;
@@ -980,12 +985,49 @@ extern "C" int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* 
     p.leaf_format = leaf_format;
     p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
     p.leaf_compact = leaf_format == PB200_LEAF_COMPACT;
-    p.n = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
+    p.n = n; p.n_starts = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length; p.T = num_neighbors;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.epoch = epoch;
     p.epoch_dev = epoch_dev;
     p.out_ids = out_ids; p.out_counts = out_counts; p.out_w = out_weights;
     p.out_nvalid = out_nvalid; p.trace_out = trace_out;
     return launch_walk(p, 0, false, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_walk_topt_indexed_multi(const uint32_t* meta, const uint32_t* idx, const uint32_t* leaf,
+                                             int leaf_format, int64_t num_nodes, const int32_t* starts, int64_t n,
+                                             int num_walks, int walk_length, int num_neighbors, uint64_t seed,
+                                             uint32_t epoch, const uint32_t* epoch_dev, int num_epochs,
+                                             int32_t* out_ids, int32_t* out_counts, float* out_weights,
+                                             int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream) {
+    PB_REQUIRE(num_epochs >= 1 && num_epochs <= 64, "walk_topt_indexed_multi: 1 <= num_epochs <= 64");
+    WalkParams probe{};
+    probe.W = num_walks; probe.L = walk_length; probe.T = num_neighbors;
+    static const bool forced_generic = [] { const char* e = getenv("PB200_WALK_VARIANT"); return e && (atoi(e) & 1); }();
+    if (num_epochs > 1 && n > 0 && leaf_format == PB200_LEAF_BUCKET && num_walks > 0 && walk_length > 0 &&
+        num_neighbors > 0 && bucket_fast_ok(probe) && !forced_generic) {
+        PB_REQUIRE(meta && leaf && starts && out_ids && out_counts && out_weights && out_nvalid,
+                   "walk_topt_indexed_multi: null pointer");
+        WalkParams p{};
+        p.leaf_format = leaf_format;
+        p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
+        p.n = n * num_epochs; p.n_starts = n; p.num_nodes = num_nodes; p.W = num_walks; p.L = walk_length;
+        p.T = num_neighbors;
+        p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.epoch = epoch; p.epoch_dev = epoch_dev;
+        p.out_ids = out_ids; p.out_counts = out_counts; p.out_w = out_weights;
+        p.out_nvalid = out_nvalid; p.trace_out = trace_out;
+        return launch_walk_bucket(p, (cudaStream_t)stream);       // ONE launch over (epoch, start) pairs
+    }
+    for (int e = 0; e < num_epochs; ++e) {                         // other formats / sizes: one launch per epoch
+        const int64_t o = (int64_t)e * n;
+        const int rc = pb200_walk_topt_indexed_ex(
+            meta, idx, leaf, leaf_format, num_nodes, starts, n, num_walks, walk_length, num_neighbors, seed,
+            epoch + (uint32_t)e, epoch_dev, out_ids ? out_ids + o * num_neighbors : nullptr,
+            out_counts ? out_counts + o * num_neighbors : nullptr, out_weights ? out_weights + o * num_neighbors : nullptr,
+            out_nvalid ? out_nvalid + o : nullptr,
+            trace_out ? trace_out + o * num_walks * walk_length : nullptr, stream);
+        if (rc) return rc;
+    }
+    return PB200_OK;
 }
 
 extern "C" int pb200_walk_topt_indexed(const uint32_t* meta, const uint32_t* idx,

@@ -49,12 +49,7 @@ class GraphedEmbeddings:
         side_up = torch.cuda.Stream(dev) if host_in else None
 
         def sample():
-            batches = []
-            for layer in range(self.layers):
-                ids, _c, w, nv = sampler._sample(nodes, num_neighbors, epoch=self.base + layer, check=False,
-                                                 epoch_dev=self.epoch_dev)
-                batches.append(NL.from_walk(ids, w, nv))
-            return batches
+            return sampler.sample_layers(nodes, num_neighbors, self.layers, epoch=self.base, epoch_dev=self.epoch_dev)
 
         def step():
             cur = torch.cuda.current_stream(dev)

@@ -181,27 +181,32 @@ def u32_add(counter, delta):
 
 
 def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epoch=0,
-              return_trace=False, use_index=True, epoch_dev=None):
+              return_trace=False, use_index=True, epoch_dev=None, num_epochs=None):
+    """Walks + visit counts + top-T.  num_epochs=E: E independent samples per start node (epochs epoch ..
+    epoch + E - 1) in one call -- one launch on the bucket index; every output gains a leading [E] dim."""
     dev = csr.device
     s = N.dev_tensor(starts, torch.int32, dev)
     n = s.numel()
     T = int(num_neighbors)
-    ids = torch.empty((n, T), dtype=torch.int32, device=dev)
-    counts = torch.empty((n, T), dtype=torch.int32, device=dev)
-    weights = torch.empty((n, T), dtype=torch.float32, device=dev)
-    nvalid = torch.empty(n, dtype=torch.int32, device=dev)
-    trace = torch.empty((n, num_walks, walk_length), dtype=torch.int32, device=dev) \
+    E = 1 if num_epochs is None else int(num_epochs)
+    lead = () if num_epochs is None else (E,)
+    ids = torch.empty(lead + (n, T), dtype=torch.int32, device=dev)
+    counts = torch.empty(lead + (n, T), dtype=torch.int32, device=dev)
+    weights = torch.empty(lead + (n, T), dtype=torch.float32, device=dev)
+    nvalid = torch.empty(lead + (n,), dtype=torch.int32, device=dev)
+    trace = torch.empty(lead + (n, num_walks, walk_length), dtype=torch.int32, device=dev) \
         if return_trace else None
-    if epoch_dev is not None and not (use_index and csr.meta is not None):
-        raise N.NativeError("walk_topt: a device-side epoch needs the sampling index (use_index=True)")
-    if use_index and csr.meta is not None:
-        check(lib().pb200_walk_topt_indexed_ex(ptr(csr.meta), ptr(csr.idx), ptr(csr.leaf),
-                                               int(getattr(csr, "leaf_format", N.LEAF_WIDE)),
-                                               csr.num_nodes, ptr(s), n, int(num_walks),
-                                               int(walk_length), T, int(seed) & (2**64 - 1),
-                                               int(epoch) & 0xFFFFFFFF, ptr(epoch_dev), ptr(ids),
-                                               ptr(counts), ptr(weights), ptr(nvalid), ptr(trace),
-                                               stream_ptr(dev)),
+    indexed = use_index and csr.meta is not None
+    if (epoch_dev is not None or num_epochs is not None) and not indexed:
+        raise N.NativeError("walk_topt: a device-side epoch / num_epochs needs the sampling index (use_index=True)")
+    if indexed:
+        check(lib().pb200_walk_topt_indexed_multi(ptr(csr.meta), ptr(csr.idx), ptr(csr.leaf),
+                                                  int(getattr(csr, "leaf_format", N.LEAF_WIDE)),
+                                                  csr.num_nodes, ptr(s), n, int(num_walks),
+                                                  int(walk_length), T, int(seed) & (2**64 - 1),
+                                                  int(epoch) & 0xFFFFFFFF, ptr(epoch_dev), E, ptr(ids),
+                                                  ptr(counts), ptr(weights), ptr(nvalid), ptr(trace),
+                                                  stream_ptr(dev)),
               "walk_topt_indexed")
         return (ids, counts, weights, nvalid, trace) if return_trace else \
             (ids, counts, weights, nvalid)

@@ -191,10 +191,7 @@ class PinSage(nn.Module):
             else:
                 xd, uploaded = x, None
             nodes = torch.arange(M, dtype=torch.int32, device=dev)
-            batches = []
-            for _ in range(self.num_layers):
-                ids, _c, w, nv = random_walk_sampler._sample(nodes, num_neighbors, check=False)
-                batches.append(NL.from_walk(ids, w, nv))
+            batches = random_walk_sampler.sample_layers(nodes, num_neighbors, self.num_layers)   # one launch
             if uploaded is not None:
                 main.wait_event(uploaded)
             emb = self.forward(xd, None, batches, None, out=out)

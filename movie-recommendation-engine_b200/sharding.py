@@ -264,14 +264,9 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     lo, hi = shard_range(num_items, rank, ws)
     dev = model._device()
     nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
-    batches = []
-    for layer in range(model.num_layers):                   # same epochs on every rank
-        ids, _c, w, nv = sampler._sample(nodes, num_neighbors, check=False, epoch_dev=epoch_dev,
-                                         epoch=None if epoch_base is None else epoch_base + layer)
-        batches.append(NL.from_walk(ids, w, nv))
-    if before_forward is not None:
-        before_forward()
-    xd = N.dev_tensor(x_local, torch.float32, dev)
+
+    def sample():                                           # same epochs on every rank; one launch for all layers
+        return sampler.sample_layers(nodes, num_neighbors, model.num_layers, epoch=epoch_base, epoch_dev=epoch_dev)
     P = lambda lin: (lin.weight, lin.bias)     # Parameter objects: identity keys the TF32 weight cache
     RND = 0 if model.precision == N.PREC_FP32 else N.EPI_ROUND_TF32     # see PinSage.forward
     PRE = 0 if model.precision == N.PREC_FP32 else N.IN_A1_TF32
@@ -279,12 +274,23 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     if _use_peer_exchange(model, dev, ws):
         srows = shard_size(num_items, ws)
         pb = peer_buffers(model.num_layers, srows, model.input_proj.out_features, dev, group)
+    rows = hi - lo
+    # Order of the two independent prologue pieces.  Device-resident features: input projection FIRST, then
+    # the walks -- by the time a rank reaches the first barrier every peer's h^(0) has long been written, so
+    # the walk kernel absorbs the skew between ranks instead of the barrier.  Host features being uploaded
+    # on a forked stream: walks first, so the upload runs under them.
+    batches = None
+    if before_forward is not None:
+        batches = sample()
+        before_forward()
+    xd = N.dev_tensor(x_local, torch.float32, dev)
+    h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision,
+                           out=pb.local(0)[:rows] if pb is not None else None)
+    if batches is None:
+        batches = sample()
     if pb is not None:
         # neighbour rows are read from their owners' memory; no all-gather.  Every layer's output is
         # written by its GEMM straight into this rank's peer-visible shard of the next layer's input.
-        rows = hi - lo
-        h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision,
-                               out=pb.local(0)[:rows])
         for i in range(model.num_layers):
             pb.barrier()                                        # every rank's h^(i) is in place
             wf, bf = model._folded_layer(i)
@@ -304,7 +310,6 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
         if check_barriers:
             pb.check()
         return emb
-    h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision)
     for i in range(model.num_layers):
         h_full = all_gather_rows(h_loc, num_items, group)   # the one exchange per layer
         wf, bf = model._folded_layer(i)

@@ -109,6 +109,24 @@ class RandomWalkSampler:
         return K.walk_topt(self.csr, nodes, self.num_walks, self.walk_length, num_neighbors,
                            self.seed, self._next_epoch() if epoch is None else epoch, epoch_dev=epoch_dev)
 
+    def sample_layers(self, nodes, num_neighbors, num_layers, epoch=None, epoch_dev=None):
+        """`num_layers` consecutive sampling calls (one per conv layer, model/pinsage.py:271-275) as ONE
+        kernel launch over (layer, start) pairs: returns [NeighborBatch] * num_layers, identical to
+        num_layers calls of batch_sample_neighbors_tensor (epochs e, e+1, ...)."""
+        if self.csr.meta is None:                       # float-weight graphs: no index, one launch per layer
+            out = []
+            for l in range(num_layers):
+                ids, _c, w, nv = self._sample(nodes, num_neighbors, check=False, epoch_dev=epoch_dev,
+                                              epoch=None if epoch is None else epoch + l)
+                out.append(NL.from_walk(ids, w, nv))
+            return out
+        if epoch is None:
+            epoch = self.epoch
+            self.epoch += num_layers
+        ids, _c, w, nv = K.walk_topt(self.csr, nodes, self.num_walks, self.walk_length, num_neighbors, self.seed,
+                                     epoch, epoch_dev=epoch_dev, num_epochs=num_layers)
+        return [NL.from_walk(ids[l], w[l], nv[l]) for l in range(num_layers)]
+
     # ---- out of scope ------------------------------------------------------------------
     def compute_ppr_matrix(self, *a, **k):
         raise NotImplementedError("compute_ppr_matrix (reference :144-195) is outside the hot path "

@@ -303,3 +303,29 @@ def test_walk_distribution_matches_the_unpatched_reference_sampler(K):
             assert abs(chi2 - df) < 4.5 * np.sqrt(2 * df) + 5, (si, step, chi2, df)
             tv = 0.5 * np.abs(a / n_walks - b / n_walks).sum()
             assert tv < 2.5 * np.sqrt(df / (2 * np.pi * n_walks)) + 0.01, (si, step, tv)
+
+
+@pytest.mark.parametrize("leaf", ["bucket", "compact"])
+def test_multi_epoch_launch_equals_separate_calls(K, leaf):
+    """num_epochs = E: one launch over (epoch, start) pairs (bucket index) or a loop of launches (tree
+    index) == E separate calls with epochs e .. e + E - 1, bitwise, traces included; sample_layers returns
+    the same NeighborBatches as consecutive batch_sample_neighbors_tensor calls."""
+    import mre_b200.synthetic as S
+    from mre_b200.utils.random_walk import RandomWalkSampler
+    ei, w = S.bipartite_graph(400, 900, 15000, seed=4)
+    csr = K.csr_build(torch.from_numpy(ei), torch.from_numpy(w), num_nodes=1300, index=leaf)
+    starts = torch.arange(0, 400, 3)
+    multi = K.walk_topt(csr, starts, 100, 2, 10, 9, 5, return_trace=True, num_epochs=3)
+    for e in range(3):
+        one = K.walk_topt(csr, starts, 100, 2, 10, 9, 5 + e, return_trace=True)
+        for a, b in zip(multi, one):
+            np.testing.assert_array_equal(_np(a[e]), _np(b))
+    if leaf == "bucket":
+        s1 = RandomWalkSampler(torch.from_numpy(ei), torch.from_numpy(w), 2, 100, seed=9, num_nodes=1300)
+        s2 = RandomWalkSampler(torch.from_numpy(ei), torch.from_numpy(w), 2, 100, seed=9, num_nodes=1300)
+        layers = s1.sample_layers(starts, 10, 2)
+        assert s1.epoch == 2
+        for l in range(2):
+            ref = s2.batch_sample_neighbors_tensor(starts, 10)
+            for a, b in zip(layers[l].as_args()[:3], ref.as_args()[:3]):
+                np.testing.assert_array_equal(_np(a), _np(b))
