@@ -197,7 +197,7 @@ def workload_config(args, inp, n_gpus):
             else f"{args.workload}: tiny synthetic graph",
             "items": inp["M"], "users": inp["U"], "ratings": inp["R"],
             "dims": [inp["F"], inp["H"], inp["E"]], "layers": inp["layers"], "num_walks": 100,
-            "walk_length": 2, "num_neighbors": 10, "parallelism": f"rows/{n_gpus}"}
+            "walk_length": 2, "num_neighbors": 10, "parallelism": f"rows/{n_gpus}" + (" (dealt round-robin)" if n_gpus > 1 else "")}
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -268,11 +268,11 @@ def main_b200(args):
     model, weights_src = model_weights(inp)
     model = model.to(dev).eval()
     model.precision = N.PRECISIONS[args.precision]
-    lo, hi = SH.shard_range(M, rank, ws)
-    x_host = inp["x"][lo:hi].contiguous().pin_memory()
+    mine = SH.local_slice(M, rank, ws) if ws > 1 else slice(0, M, 1)     # rows dealt round-robin to the ranks
+    x_host = inp["x"][mine].contiguous().pin_memory()
     x_dev = x_host.to(dev)
-    out_host = torch.empty((hi - lo, inp["E"]), dtype=torch.float32).pin_memory()
-    nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+    out_host = torch.empty((x_host.size(0), inp["E"]), dtype=torch.float32).pin_memory()
+    nodes = torch.arange(mine.start, mine.stop, mine.step or 1, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -319,15 +319,15 @@ def main_b200(args):
     sharded_equals_single = None
     if ws > 1:
         e0 = sampler.epoch
-        mine = SH.get_embeddings_sharded(model, x_dev, sampler, M, T)
-        full = SH.all_gather_rows(mine, M)
+        emb_mine = SH.get_embeddings_sharded(model, x_dev, sampler, M, T)
+        full = SH.all_gather_rows(emb_mine, M, layout=SH.EMB_LAYOUT)
         if rank == 0:
             sampler.epoch = e0
             single = model.get_embeddings(inp["x"].to(dev), sampler, T)
             sharded_equals_single = bool(torch.equal(full, single))
             del single
         sampler.epoch = e0 + layers
-        del full, mine
+        del full, emb_mine
         barrier()
 
     if ws > 1 and not args.no_graph:

@@ -214,6 +214,15 @@ int pb200_pool_sharded(const float* const* shard_ptrs, int world, int64_t shard_
                        int dim, const int32_t* ids, const float* weights, const int32_t* list_len,
                        const int32_t* weight_len, int64_t n, int max_neighbors, int mode, float* out,
                        pb200_stream_t stream);
+/* Same with a choice of row layout.  BLOCKS: row i on rank i / shard_rows (local row i % shard_rows).  CYCLIC: row i
+ * on rank i % world (local row i / world) -- rows dealt round-robin, which balances a popularity-sorted catalogue
+ * across ranks (contiguous blocks give rank 0 all the heavy rows of the walk kernel). */
+#define PB200_SHARD_BLOCKS 0
+#define PB200_SHARD_CYCLIC 1
+int pb200_pool_sharded_ex(const float* const* shard_ptrs, int world, int64_t shard_rows, int64_t num_rows,
+                          int dim, const int32_t* ids, const float* weights, const int32_t* list_len,
+                          const int32_t* weight_len, int64_t n, int max_neighbors, int mode, int layout,
+                          float* out, pb200_stream_t stream);
 
 /* Exchange buffers for pb200_pool_sharded: plain cudaMalloc allocations exported / opened
  * through CUDA IPC (one process per GPU on one box).  Handles are opaque 64-byte blobs that the

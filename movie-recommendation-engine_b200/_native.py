@@ -57,6 +57,8 @@ SIGNATURES = {
                            c_ptr, c_ptr]),
     "pb200_pool_sharded": (c_int, [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                    c_int, c_int, c_ptr, c_ptr]),
+    "pb200_pool_sharded_ex": (c_int, [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                                      c_int, c_int, c_int, c_ptr, c_ptr]),
     "pb200_peer_alloc": (c_int, [c_size, c_ptr]),
     "pb200_peer_free": (c_int, [c_ptr]),
     "pb200_peer_export": (c_int, [c_ptr, c_ptr]),
@@ -111,6 +113,7 @@ POOL_ROUND_TF32 = 0x100
 PREC_FP32, PREC_TF32, PREC_AUTO = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "auto": PREC_AUTO}
 METRIC_IP, METRIC_L2 = 0, 1
+SHARD_BLOCKS, SHARD_CYCLIC = 0, 1
 LEAF_WIDE, LEAF_COMPACT, LEAF_BUCKET = 0, 1, 2          # sampling-index leaf formats (pb200_walk_index_build_ex)
 
 _lib = None

@@ -22,11 +22,21 @@ __device__ __forceinline__ float round_tf32(float f) {
 // mapped into this process by CUDA IPC; a neighbour row is read straight from its owner over
 // NVLink (16-byte vector loads, ~1.3 valid rows per node on the bipartite graph) instead of
 // all-gathering the whole h matrix every layer.  world == 0: plain single-buffer x.
+// cyclic: row i lives on rank i % world at local row i / world (items dealt round-robin: on a
+// popularity-sorted catalogue contiguous blocks give rank 0 all the heavy rows); else blocks.
 struct PeerMap {
     const float* base[PB200_MAX_PEERS];
     int64_t shard_rows;
     int world;
+    int cyclic;
 };
+
+__device__ __forceinline__ const float* peer_row(const PeerMap& pm, int id, int dim) {
+    int owner, local;
+    if (pm.cyclic) { local = id / pm.world; owner = id - local * pm.world; }
+    else { owner = (int)(id / pm.shard_rows); local = (int)(id - owner * pm.shard_rows); }
+    return pm.base[owner] + (int64_t)local * dim;
+}
 
 template <bool kVec>
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, int dim,
@@ -50,8 +60,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
                 for (int r = 0; r < nv; ++r) {
                     const float* xr;
                     if (pm.world > 0) {
-                        const int owner = (int)(s_id[r] / pm.shard_rows);
-                        xr = pm.base[owner] + ((int64_t)s_id[r] - owner * pm.shard_rows) * dim;
+                        xr = peer_row(pm, s_id[r], dim);
                     } else {
                         xr = x + (int64_t)s_id[r] * dim;
                     }
@@ -77,8 +86,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
                 for (int r = 0; r < nv; ++r) {
                     const float* xr;
                     if (pm.world > 0) {
-                        const int owner = (int)(s_id[r] / pm.shard_rows);
-                        xr = pm.base[owner] + ((int64_t)s_id[r] - owner * pm.shard_rows) * dim;
+                        xr = peer_row(pm, s_id[r], dim);
                     } else {
                         xr = x + (int64_t)s_id[r] * dim;
                     }
@@ -130,21 +138,30 @@ extern "C" int pb200_pool(const float* x, int64_t num_rows, int dim, const int32
                        out, (cudaStream_t)stream);
 }
 
-extern "C" int pb200_pool_sharded(const float* const* shard_ptrs, int world, int64_t shard_rows,
-                                  int64_t num_rows, int dim, const int32_t* ids, const float* weights,
-                                  const int32_t* list_len, const int32_t* weight_len, int64_t n,
-                                  int max_neighbors, int mode, float* out, pb200_stream_t stream) {
+extern "C" int pb200_pool_sharded_ex(const float* const* shard_ptrs, int world, int64_t shard_rows,
+                                     int64_t num_rows, int dim, const int32_t* ids, const float* weights,
+                                     const int32_t* list_len, const int32_t* weight_len, int64_t n,
+                                     int max_neighbors, int mode, int layout, float* out, pb200_stream_t stream) {
     PB_REQUIRE(shard_ptrs && world >= 1 && world <= PB200_MAX_PEERS && shard_rows > 0,
                "pool_sharded: need 1..%d shard pointers and shard_rows > 0", PB200_MAX_PEERS);
     PB_REQUIRE(num_rows <= (int64_t)world * shard_rows, "pool_sharded: num_rows exceeds world * shard_rows");
+    PB_REQUIRE(layout == PB200_SHARD_BLOCKS || layout == PB200_SHARD_CYCLIC, "pool_sharded: unknown layout %d", layout);
     PeerMap pm{};
     for (int r = 0; r < world; ++r) {
         PB_REQUIRE(shard_ptrs[r], "pool_sharded: shard pointer %d is null", r);
         pm.base[r] = shard_ptrs[r];
     }
-    pm.shard_rows = shard_rows; pm.world = world;
+    pm.shard_rows = shard_rows; pm.world = world; pm.cyclic = layout == PB200_SHARD_CYCLIC;
     return pool_launch(nullptr, pm, num_rows, dim, ids, weights, list_len, weight_len, n, max_neighbors,
                        mode, out, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_pool_sharded(const float* const* shard_ptrs, int world, int64_t shard_rows,
+                                  int64_t num_rows, int dim, const int32_t* ids, const float* weights,
+                                  const int32_t* list_len, const int32_t* weight_len, int64_t n,
+                                  int max_neighbors, int mode, float* out, pb200_stream_t stream) {
+    return pb200_pool_sharded_ex(shard_ptrs, world, shard_rows, num_rows, dim, ids, weights, list_len, weight_len, n,
+                                 max_neighbors, mode, PB200_SHARD_BLOCKS, out, stream);
 }
 
 // ---- barrier between the ranks of one box on peer memory (a plain kernel: CUDA-graph capturable) ----

@@ -44,8 +44,8 @@ class GraphedEmbeddings:
         self.base = int(sampler.epoch)
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         n_items = x.size(0) if num_items is None else int(num_items)
-        lo, hi = SH.shard_range(n_items, rank, ws)
-        nodes = self.nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+        sl = SH.local_slice(n_items, rank, ws) if ws > 1 else slice(0, n_items, 1)
+        nodes = self.nodes = torch.arange(sl.start, sl.stop, sl.step or 1, dtype=torch.int32, device=dev)
         side_up = torch.cuda.Stream(dev) if host_in else None
 
         def sample():

@@ -244,13 +244,13 @@ def pool(x, ids, weights, list_len, weight_len, mode):
 
 
 def pool_sharded(shard_ptr_array, world, shard_rows, num_rows, dim, ids, weights, list_len, weight_len, mode,
-                 dev):
+                 dev, layout=N.SHARD_BLOCKS):
     """pb200_pool over a row-sharded x whose shards live on the ranks of one box (peer memory)."""
     n, T = ids.shape
     out = torch.empty((n, dim), dtype=torch.float32, device=dev)
-    check(lib().pb200_pool_sharded(shard_ptr_array, world, shard_rows, num_rows, dim, ptr(ids), ptr(weights),
-                                   ptr(list_len), ptr(weight_len), n, T, mode, ptr(out), stream_ptr(dev)),
-          "pool_sharded")
+    check(lib().pb200_pool_sharded_ex(shard_ptr_array, world, shard_rows, num_rows, dim, ptr(ids), ptr(weights),
+                                      ptr(list_len), ptr(weight_len), n, T, mode, int(layout), ptr(out),
+                                      stream_ptr(dev)), "pool_sharded")
     return out
 
 

@@ -41,11 +41,42 @@ def shard_range(n, rank, world_size):
     return lo, min(lo + s, n)
 
 
-def all_gather_rows(local, n_total, group=None):
-    """Row shards (shard_range layout) -> the full [n_total, ...] tensor on every rank."""
+# How the rows of the embedding step (start nodes of the walks = rows of x, h and the embeddings) are dealt
+# to ranks.  "cyclic": row i belongs to rank i % world -- the catalogues this path sees are popularity
+# sorted (MovieLens ids, the synthetic generator), and the heavy rows cost the walk kernel ~20 % more
+# (more distinct buckets per start row: more DRAM misses), so contiguous blocks make rank 0 the slowest
+# rank of every step (r2 measurement at N = 2: 203 us vs 166 us).  "blocks": shard_range.
+EMB_LAYOUT = "cyclic"
+
+
+def local_slice(n, rank, world_size, layout=None):
+    """The rows of an n-row matrix that rank owns, as a slice."""
+    if (layout or EMB_LAYOUT) == "cyclic":
+        return slice(rank, n, world_size)
+    lo, hi = shard_range(n, rank, world_size)
+    return slice(lo, hi)
+
+
+def local_rows(t, group=None, layout=None):
+    """This rank's rows of a full [n, ...] tensor."""
+    rank, ws = world(group)
+    return t[local_slice(t.size(0), rank, ws, layout)]
+
+
+def all_gather_rows(local, n_total, group=None, layout="blocks"):
+    """Row shards (shard_range layout, or cyclic) -> the full [n_total, ...] tensor on every rank."""
     rank, ws = world(group)
     if ws == 1:
         return local
+    if layout == "cyclic":
+        s = shard_size(n_total, ws)
+        if local.size(0) != s:
+            pad = torch.zeros((s - local.size(0),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            local = torch.cat([local, pad])
+        out = torch.empty((ws, s) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view((ws * s,) + tuple(local.shape[1:])), local.contiguous(), group=group)
+        # out[r, j] = row r + j * ws
+        return out.transpose(0, 1).reshape((ws * s,) + tuple(local.shape[1:]))[:n_total].contiguous()
     s = shard_size(n_total, ws)
     if local.size(0) != s:                                  # pad the tail shard
         pad = torch.zeros((s - local.size(0),) + tuple(local.shape[1:]), dtype=local.dtype,
@@ -247,9 +278,11 @@ def _use_peer_exchange(model, dev, ws):
 
 
 def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None,
-                           epoch_base=None, epoch_dev=None, check_barriers=True, before_forward=None):
+                           epoch_base=None, epoch_dev=None, check_barriers=True, before_forward=None,
+                           layout=None):
     """PinSage.get_embeddings with rows split across ranks.  x_local: this rank's rows of the
-    feature matrix (shard_range layout).  Returns this rank's rows of the embeddings.
+    feature matrix (``local_rows(x)``: EMB_LAYOUT, cyclic by default).  Returns this rank's rows of the
+    embeddings (same layout; ``all_gather_rows(emb, n, layout=EMB_LAYOUT)`` reassembles them).
     epoch_base / epoch_dev: fixed host epoch + device-side counter (CUDA-graph capture, see
     graphs.GraphedEmbeddings); by default the sampler's own epoch counter advances.
     check_barriers: read the peer barriers' time-out flag after the step (one stream sync) and raise
@@ -261,9 +294,10 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     from . import kernels as K
     from . import neighbor_lists as NL
     rank, ws = world(group)
-    lo, hi = shard_range(num_items, rank, ws)
+    layout = layout or EMB_LAYOUT
+    mine_rows = local_slice(num_items, rank, ws, layout)
     dev = model._device()
-    nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+    nodes = torch.arange(mine_rows.start, mine_rows.stop, mine_rows.step or 1, dtype=torch.int32, device=dev)
 
     def sample():                                           # same epochs on every rank; one launch for all layers
         return sampler.sample_layers(nodes, num_neighbors, model.num_layers, epoch=epoch_base, epoch_dev=epoch_dev)
@@ -274,7 +308,7 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     if _use_peer_exchange(model, dev, ws):
         srows = shard_size(num_items, ws)
         pb = peer_buffers(model.num_layers, srows, model.input_proj.out_features, dev, group)
-    rows = hi - lo
+    rows = nodes.numel()
     # Order of the two independent prologue pieces.  Device-resident features: input projection FIRST, then
     # the walks -- by the time a rank reaches the first barrier every peer's h^(0) has long been written, so
     # the walk kernel absorbs the skew between ranks instead of the barrier.  Host features being uploaded
@@ -296,7 +330,8 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
             wf, bf = model._folded_layer(i)
             ids, wts, ll, wl = batches[i].as_args()
             h_neigh = K.pool_sharded(pb.ptr_array(i), ws, srows, num_items, h_loc.size(1), ids, wts, ll, wl,
-                                     N.POOL_PINSAGE | N.POOL_ROUND_TF32, dev)
+                                     N.POOL_PINSAGE | N.POOL_ROUND_TF32, dev,
+                                     layout=N.SHARD_CYCLIC if layout == "cyclic" else N.SHARD_BLOCKS)
             h_loc = K.gather_dense(h_loc, wf, bf, a2=h_neigh,
                                    flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
                                    precision=model.precision,
@@ -311,15 +346,15 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
             pb.check()
         return emb
     for i in range(model.num_layers):
-        h_full = all_gather_rows(h_loc, num_items, group)   # the one exchange per layer
+        h_full = all_gather_rows(h_loc, num_items, group, layout)   # the one exchange per layer
         wf, bf = model._folded_layer(i)
         if model.precision != N.PREC_FP32 and not model.fuse_pool:      # see PinSage.forward
             h_neigh = K.pool(h_full, *batches[i].as_args(), N.POOL_PINSAGE | N.POOL_ROUND_TF32)
-            h_loc = K.gather_dense(h_full[lo:hi], wf, bf, a2=h_neigh,
+            h_loc = K.gather_dense(h_full[mine_rows].contiguous(), wf, bf, a2=h_neigh,
                                    flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
                                    precision=model.precision)
             continue
-        h_loc = K.gather_dense(h_full[lo:hi], wf, bf, pool_x=h_full, lists=batches[i].as_args(),
+        h_loc = K.gather_dense(h_full[mine_rows].contiguous(), wf, bf, pool_x=h_full, lists=batches[i].as_args(),
                                pool_mode=N.POOL_PINSAGE, flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE,
                                precision=model.precision)
     return K.gather_dense(h_loc, *P(model.output_proj), flags=N.EPI_L2NORM | PRE,

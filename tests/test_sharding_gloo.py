@@ -30,6 +30,12 @@ def _worker(rank, world, port, n_items):
         full = torch.arange(n_items * 3, dtype=torch.float32).reshape(n_items, 3)
         got = SH.all_gather_rows(full[lo:hi].clone(), n_items)
         assert torch.equal(got, full)
+        # --- cyclic layout (rows dealt round-robin: the embedding step's default) ---
+        assert SH.EMB_LAYOUT == "cyclic"
+        mine = SH.local_rows(full)
+        assert torch.equal(mine, full[rank::world]) and mine.size(0) <= SH.shard_size(n_items, world)
+        got = SH.all_gather_rows(mine.clone(), n_items, layout="cyclic")
+        assert torch.equal(got, full)
         # --- item-sharded exact search: local top-k with global ids, gather, merge ---
         rng = np.random.Generator(np.random.PCG64(0))
         x = rng.standard_normal((n_items, 16)).astype(np.float32)

@@ -23,18 +23,35 @@ for prec in (N.PREC_FP32, N.PREC_AUTO):
     full = model.get_embeddings(x.to(dev), sampler, 10)                 # every rank: unsharded
     sampler.epoch = 0
     lo, hi = SH.shard_range(M, rank, ws)
-    mine = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
-    assert torch.equal(mine, full[lo:hi]), f"rank {rank}: sharded embeddings differ (precision {prec})"
+    for layout in ("cyclic", "blocks"):
+        sampler.epoch = 0
+        rows = SH.local_slice(M, rank, ws, layout)
+        mine = SH.get_embeddings_sharded(model, x[rows], sampler, M, 10, layout=layout)
+        assert torch.equal(mine, full[rows]), f"rank {rank}: sharded embeddings differ (precision {prec}, {layout})"
+        back = SH.all_gather_rows(mine, M, layout=layout)
+        assert torch.equal(back, full), f"rank {rank}: all_gather_rows({layout}) does not reassemble the matrix"
+rows = SH.local_slice(M, rank, ws)
 # CUDA-graph replays of the sharded step == eager sharded calls with the same epochs
 from mre_b200.graphs import GraphedEmbeddings
 model.precision = N.PREC_AUTO
 sampler.epoch = 100
-g = GraphedEmbeddings(model, x[lo:hi].to(dev), sampler, 10, num_items=M)
+g = GraphedEmbeddings(model, x[rows].to(dev), sampler, 10, num_items=M)
 for k in range(3):
     got = g.replay().clone()
     sampler.epoch = 100 + 2 * k
-    want = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
+    want = SH.get_embeddings_sharded(model, x[rows], sampler, M, 10)
     assert torch.equal(got, want), f"rank {rank}: graph replay {k} differs from the eager step"
+# pinned host features in, pinned host embeddings out (upload forked under the walks, download at the end)
+xh = x[rows].contiguous().pin_memory()
+oh = torch.empty((xh.size(0), E_), dtype=torch.float32).pin_memory()
+sampler.epoch = 200
+gh = GraphedEmbeddings(model, xh, sampler, 10, num_items=M, out=oh)
+for k in range(2):
+    got = gh.replay()
+    torch.cuda.synchronize()
+    sampler.epoch = 200 + 2 * k
+    want = SH.get_embeddings_sharded(model, x[rows], sampler, M, 10)
+    assert got is oh and torch.equal(got, want.cpu()), f"rank {rank}: host-buffer graph replay {k} differs"
 # a rank that cannot set up peer memory: ALL ranks must fall back to the all-gather exchange
 os.environ["PB200_TEST_PEER_FAIL_RANK"] = "1"
 SH._PEER_CACHE.clear()                       # (leaks the earlier buffers: test only)
@@ -42,9 +59,9 @@ import warnings
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     sampler.epoch = 0
-    mine_fb = SH.get_embeddings_sharded(model, x[lo:hi], sampler, M, 10)
+    mine_fb = SH.get_embeddings_sharded(model, x[rows], sampler, M, 10)
 assert all(not pb.ok for pb in SH._PEER_CACHE.values()), f"rank {rank}: fallback was not collective"
-assert torch.equal(mine_fb, full[lo:hi]), f"rank {rank}: all-gather fallback differs"
+assert torch.equal(mine_fb, full[rows]), f"rank {rank}: all-gather fallback differs"
 del os.environ["PB200_TEST_PEER_FAIL_RANK"]
 SH._PEER_CACHE.clear()
 emb = full

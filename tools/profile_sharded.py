@@ -23,10 +23,11 @@ sampler = RandomWalkSampler(torch.from_numpy(inp["ei"]), torch.from_numpy(inp["w
                             num_nodes=M + inp["U"])
 model, _ = bench.model_weights(inp)
 model = model.to(dev).eval()
-lo, hi = SH.shard_range(M, rank, ws)
-rows = hi - lo
-xd = inp["x"][lo:hi].to(dev)
-nodes = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+mine = SH.local_slice(M, rank, ws)
+xd = inp["x"][mine].to(dev)
+rows = xd.size(0)
+nodes = torch.arange(mine.start, mine.stop, mine.step or 1, dtype=torch.int32, device=dev)
+CYC = N.SHARD_CYCLIC if SH.EMB_LAYOUT == "cyclic" else N.SHARD_BLOCKS
 for _ in range(3):
     SH.get_embeddings_sharded(model, xd, sampler, M, T)
 srows = SH.shard_size(M, ws)
@@ -49,7 +50,7 @@ for rep in range(20):
         pb.barrier(); mark(f"barrier{i}")
         wf, bf = model._folded_layer(i)
         ids, wts, ll, wl = batches[i].as_args()
-        hn = K.pool_sharded(pb.ptr_array(i), ws, srows, M, h.size(1), ids, wts, ll, wl, N.POOL_PINSAGE | N.POOL_ROUND_TF32, dev)
+        hn = K.pool_sharded(pb.ptr_array(i), ws, srows, M, h.size(1), ids, wts, ll, wl, N.POOL_PINSAGE | N.POOL_ROUND_TF32, dev, layout=CYC)
         mark(f"pool{i}")
         h = K.gather_dense(h, wf, bf, a2=hn, flags=N.EPI_RELU | N.EPI_L2NORM | RND | PRE | N.IN_A2_TF32,
                            precision=model.precision, out=pb.local(i + 1)[:rows] if i + 1 < model.num_layers else None)
