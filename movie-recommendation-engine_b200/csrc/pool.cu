@@ -53,32 +53,59 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ x, 
         const int nv = prepare_list(a, row, s_id, s_w, lane);
         float* o = out + row * dim;
         if (kVec) {
-            for (int c = lane * 4; c < dim; c += 128) {
-                float4 acc = is_max && nv ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+            // All column chunks of a neighbour row are requested together (dim <= 512: 4 x 16 B per lane in
+            // flight), and two neighbour rows per iteration: a row shard on another GPU costs one NVLink round
+            // trip per REQUEST WAVE, not per chunk (r2: pool_sharded 31 us vs 11 us with local pointers when
+            // the chunks were fetched one after the other).
+            for (int c0 = lane * 4; c0 < dim; c0 += 512) {
+                float4 acc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[k] = is_max && nv ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                for (int r = 0; r < nv; ++r) {
-                    const float* xr;
-                    if (pm.world > 0) {
-                        xr = peer_row(pm, s_id[r], dim);
-                    } else {
-                        xr = x + (int64_t)s_id[r] * dim;
+                for (int r = 0; r < nv; r += 2) {
+                    const bool two = r + 1 < nv;
+                    const float* xa = pm.world > 0 ? peer_row(pm, s_id[r], dim) : x + (int64_t)s_id[r] * dim;
+                    const float* xb = !two ? xa : (pm.world > 0 ? peer_row(pm, s_id[r + 1], dim) : x + (int64_t)s_id[r + 1] * dim);
+                    float4 va[4], vb[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = c0 + 128 * k;
+                        va[k] = c < dim ? __ldg(reinterpret_cast<const float4*>(xa + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        vb[k] = (two && c < dim) ? __ldg(reinterpret_cast<const float4*>(xb + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
-                    if (is_max) {
-                        acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
-                        acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
-                    } else {
-                        const float w = s_w[r];
-                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    const float wa = is_max ? 0.f : s_w[r], wb = (is_max || !two) ? 0.f : s_w[r + 1];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (is_max) {
+                            acc[k].x = fmaxf(acc[k].x, va[k].x); acc[k].y = fmaxf(acc[k].y, va[k].y);
+                            acc[k].z = fmaxf(acc[k].z, va[k].z); acc[k].w = fmaxf(acc[k].w, va[k].w);
+                            if (two) {
+                                acc[k].x = fmaxf(acc[k].x, vb[k].x); acc[k].y = fmaxf(acc[k].y, vb[k].y);
+                                acc[k].z = fmaxf(acc[k].z, vb[k].z); acc[k].w = fmaxf(acc[k].w, vb[k].w);
+                            }
+                        } else {                         // same order of additions as before: row r, then row r + 1
+                            acc[k].x = fmaf(wa, va[k].x, acc[k].x); acc[k].y = fmaf(wa, va[k].y, acc[k].y);
+                            acc[k].z = fmaf(wa, va[k].z, acc[k].z); acc[k].w = fmaf(wa, va[k].w, acc[k].w);
+                            if (two) {
+                                acc[k].x = fmaf(wb, vb[k].x, acc[k].x); acc[k].y = fmaf(wb, vb[k].y, acc[k].y);
+                                acc[k].z = fmaf(wb, vb[k].z, acc[k].z); acc[k].w = fmaf(wb, vb[k].w, acc[k].w);
+                            }
+                        }
                     }
                 }
-                if (round_out) {
-                    acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y);
-                    acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = c0 + 128 * k;
+                    if (c < dim) {
+                        float4 a4 = acc[k];
+                        if (round_out) {
+                            a4.x = round_tf32(a4.x); a4.y = round_tf32(a4.y);
+                            a4.z = round_tf32(a4.z); a4.w = round_tf32(a4.w);
+                        }
+                        *reinterpret_cast<float4*>(o + c) = a4;
+                    }
                 }
-                *reinterpret_cast<float4*>(o + c) = acc;
             }
         } else {
             for (int c = lane; c < dim; c += 32) {

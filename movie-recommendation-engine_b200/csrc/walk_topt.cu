@@ -814,12 +814,19 @@ static bool bucket_fast_ok(const WalkParams& p) { return p.W * p.L <= 200 && p.T
 static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
     // tuning knobs (tools/tune_walk.py): PB200_WALK_MINBLOCKS = 6 | 7 | 8 (register cap),
     // PB200_WALK_TABLE = 10 * select version + insert version
-    static const int minb = [] { const char* e = getenv("PB200_WALK_MINBLOCKS"); return e ? atoi(e) : 6; }();
+    static const int minb_env = [] { const char* e = getenv("PB200_WALK_MINBLOCKS"); return e ? atoi(e) : 6; }();
     static const int var = [] { const char* e = getenv("PB200_WALK_TABLE"); return e ? atoi(e) : PB200_WALK_TABLE_DEFAULT; }();
     PhiloxKeys pk;
     philox_round_keys(p.seed_lo, p.seed_hi, pk);
     // PB200_WALK_BATCH = walks per lane in flight (0 = the one-walk kernel); PB200_WALK_LD = 0 | 2
-    static const int batch = [] { const char* e = getenv("PB200_WALK_BATCH"); return e ? atoi(e) : PB200_WALK_BATCH_DEFAULT; }();
+    static const int batch_env = [] { const char* e = getenv("PB200_WALK_BATCH"); return e ? atoi(e) : -1; }();
+    static const bool minb_set = getenv("PB200_WALK_MINBLOCKS") != nullptr;
+    // Default: 2 walks per lane in flight at 6 blocks / SM; launches that cannot fill the GPU several times
+    // (a shard of a multi-GPU step) are latency bound and take 4 walks per lane at 4 blocks / SM instead
+    // (r2_tune13: 7,803 starts x 2 samples 80 -> 59 us; 62,423 x 2: 334 vs 336 us).
+    const bool small = p.n <= (int64_t)kSMs * 48 * 9;
+    const int batch = batch_env >= 0 ? batch_env : (small ? 4 : PB200_WALK_BATCH_DEFAULT);
+    const int minb = minb_set ? minb_env : (batch == 4 ? 4 : 6);
     static const int ld = [] { const char* e = getenv("PB200_WALK_LD"); return e ? atoi(e) : 2; }();
     if (batch > 0) {
         const int64_t cap = (int64_t)kSMs * 32;

@@ -20,15 +20,16 @@ d = np.load("/tmp/c2_graph.npz")
 t0 = time.time()
 csr = K.csr_build(torch.from_numpy(d["ei"]), torch.from_numpy(d["w"]), num_nodes=int(d["N"]))
 torch.cuda.synchronize(); t_build = time.time() - t0
-nodes = torch.arange(62423, dtype=torch.int32, device="cuda")
+nodes = torch.arange(0, 62423, int(os.environ.get("TUNE_STRIDE", "1")), dtype=torch.int32, device="cuda")
+E = int(os.environ.get("TUNE_E", "0")) or None
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 W = int(os.environ.get("TUNE_W", "100")); L = int(os.environ.get("TUNE_L", "2"))
-for _ in range(3): K.walk_topt(csr, nodes, W, L, 10, 1234, 0)
+for _ in range(3): K.walk_topt(csr, nodes, W, L, 10, 1234, 0, num_epochs=E)
 ts = []
 for e in range(10):
     flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); out = K.walk_topt(csr, nodes, W, L, 10, 1234, e); b.record()
+    a.record(); out = K.walk_topt(csr, nodes, W, L, 10, 1234, e, num_epochs=E); b.record()
     torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
 chk = int(out[0].long().sum()) ^ (int(out[1].long().sum()) << 20) ^ int((out[2].double() * 1e6).sum().item())
 print("variant", %r, "l2fetch", NV.lib().pb200_get_l2_fetch_granularity(), "walk_ms mean %%.4f min %%.4f chk %%d index_MB %%.0f fmt %%d build_s %%.2f" %% (
