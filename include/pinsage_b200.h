@@ -171,6 +171,39 @@ int pb200_walk_topt_indexed_multi(const uint32_t* meta, const uint32_t* idx, con
                                   float* out_weights, int32_t* out_nvalid, int32_t* trace_out, pb200_stream_t stream);
 int pb200_u32_add(uint32_t* counter, uint32_t delta, pb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * N4  GraphBuilder.build_item_similarity_graph          (data/graph_builder.py:59-116)
+ * Item-item co-occurrence graph: pairs of movies rated together by >= threshold users, both directions,
+ * weight = the count, pairs in the order of their FIRST co-occurrence (users ascending, position pairs
+ * i < j of the user's rows lexicographic) -- the reference's dict order.
+ *   pb200_cooc_pairs: urow_ptr / uitems = user -> movies CSR (rows of the ratings table in table order),
+ *     irow_ptr / iusers / ipos = movie -> (user rank ascending, position of the movie in that user's row);
+ *     acc_cnt / acc_first: int32 [num_blocks, num_items] scratch; emits up to `capacity` pairs (a < b) with their
+ *     order key, count; *out_count (device uint64) = number of qualifying pairs (may exceed capacity: retry).
+ *   pb200_cooc_edges: sorts the pairs by key (cub radix sort) and writes edge_index int64 [2, 2P]
+ *     = (a -> b), (b -> a) per pair and edge_weight float32 [2P].
+ * ------------------------------------------------------------------------------------ */
+int pb200_cooc_pairs(const int64_t* urow_ptr, const int32_t* uitems, const int64_t* irow_ptr, const int32_t* iusers,
+                     const int32_t* ipos, int64_t num_users, int64_t num_items, int threshold, int bits_pos,
+                     int32_t* acc_cnt, int32_t* acc_first, int num_blocks, uint64_t* out_key, int32_t* out_a,
+                     int32_t* out_b, int32_t* out_cnt, uint64_t capacity, uint64_t* out_count, pb200_stream_t stream);
+size_t pb200_cooc_edges_workspace_bytes(int64_t num_pairs);
+int pb200_cooc_edges(const uint64_t* keys, const int32_t* a, const int32_t* b, const int32_t* cnt, int64_t num_pairs,
+                     int64_t* edge_index, float* edge_weight, void* workspace, size_t workspace_bytes,
+                     pb200_stream_t stream);
+
+/* N4  RandomWalkSampler.compute_ppr_matrix / precompute_top_neighbors
+ *                                                                  (utils/random_walk.py:144-229)
+ * pb200_ppr_push: per source, num_iterations in-place push sweeps over all nodes in index order (alpha =
+ * teleport probability) on the CSR of pb200_csr_build; ppr_out / residual_ws: float64 [num_sources, vec_len]
+ * (vec_len >= num_nodes: the reference sizes the vectors max(edge_index.max() + 1, max(nodes) + 1)).
+ * pb200_topk_rows_f64: per row the k largest strictly positive scores, ties by smaller index; -1 / 0.0 padding. */
+int pb200_ppr_push(const int64_t* row_ptr, const int32_t* col, const void* cum, int cum_kind, int quant_shift,
+                   int64_t num_nodes, int64_t vec_len, const int32_t* sources, int64_t num_sources, double alpha,
+                   int num_iterations, double* ppr_out, double* residual_ws, pb200_stream_t stream);
+int pb200_topk_rows_f64(const double* scores, int64_t num_rows, int64_t row_len, int k, int32_t* out_ids,
+                        double* out_scores, pb200_stream_t stream);
+
 /* Counting stage alone, given traces (parity "given the same walk traces"):
  * trace int32 [n, V] (V = W*L visits in walk-major order, -1 = none). */
 int pb200_count_topt(const int32_t* trace, int64_t n, int visits_per_start, int num_neighbors,

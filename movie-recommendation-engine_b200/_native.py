@@ -53,6 +53,13 @@ SIGNATURES = {
                                               c_ptr]),
     "pb200_u32_add": (c_int, [c_ptr, c_u32, c_ptr]),
     "pb200_count_topt": (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "pb200_cooc_pairs": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_int,
+                                 c_ptr, c_ptr, c_ptr, c_ptr, c_u64, c_ptr, c_ptr]),
+    "pb200_cooc_edges_workspace_bytes": (c_size, [c_i64]),
+    "pb200_cooc_edges": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "pb200_ppr_push": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_i64, c_ptr, c_i64, ctypes.c_double, c_int,
+                               c_ptr, c_ptr, c_ptr]),
+    "pb200_topk_rows_f64": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "pb200_pool": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int,
                            c_ptr, c_ptr]),
     "pb200_pool_sharded": (c_int, [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,

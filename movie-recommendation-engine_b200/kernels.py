@@ -218,6 +218,86 @@ def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epo
     return (ids, counts, weights, nvalid, trace) if return_trace else (ids, counts, weights, nvalid)
 
 
+def ppr_push(csr: CSR, sources, alpha=0.15, num_iterations=10, vec_len=None):
+    """Dense PPR push scores (pb200_ppr_push): float64 [len(sources), vec_len] on the device."""
+    dev = csr.device
+    s = N.dev_tensor(sources, torch.int32, dev).reshape(-1)
+    vec_len = csr.num_nodes if vec_len is None else max(int(vec_len), csr.num_nodes)
+    ppr = torch.empty((s.numel(), vec_len), dtype=torch.float64, device=dev)
+    res = torch.empty((s.numel(), vec_len), dtype=torch.float64, device=dev)
+    check(lib().pb200_ppr_push(ptr(csr.row_ptr), ptr(csr.col) if csr.num_edges else ptr(csr.row_ptr),
+                               ptr(csr.cum) if csr.num_edges else ptr(csr.row_ptr), csr.cum_kind,
+                               max(csr.quant_shift, 0), csr.num_nodes, vec_len, ptr(s), s.numel(), float(alpha),
+                               int(num_iterations), ptr(ppr), ptr(res), stream_ptr(dev)), "ppr_push")
+    return ppr
+
+
+def topk_rows_f64(scores, k):
+    """Per row: the k largest strictly positive float64 scores, ties by smaller index (ids -1 / score 0 padded)."""
+    dev = N.device_of(scores)
+    sc = N.dev_tensor(scores, torch.float64, dev)
+    S, n = sc.shape
+    ids = torch.empty((S, k), dtype=torch.int32, device=dev)
+    vals = torch.empty((S, k), dtype=torch.float64, device=dev)
+    check(lib().pb200_topk_rows_f64(ptr(sc), S, n, int(k), ptr(ids), ptr(vals), stream_ptr(dev)), "topk_rows_f64")
+    return ids, vals
+
+
+def item_cooccurrence_graph(user_rank, movie_idx, num_users, num_items, threshold, device=None):
+    """Item-item co-occurrence graph (pb200_cooc_*; reference data/graph_builder.py:59-116) from the ratings
+    table given as (user rank, movie index) per row, in table order.  Returns (src int64 [2P], dst int64 [2P],
+    weight float32 [2P]) on the device, pairs in the reference's dict order."""
+    dev = N.device_of(user_rank, movie_idx, device=device)
+    u = N.dev_tensor(user_rank, torch.int64, dev).reshape(-1)
+    m = N.dev_tensor(movie_idx, torch.int64, dev).reshape(-1)
+    R = u.numel()
+    if R and int(torch.unique(u * num_items + m).numel()) != R:
+        raise ValueError("build_item_similarity_graph: a user rates the same movie more than once "
+                         "(unsupported: MovieLens ratings are unique per (user, movie))")
+    st = stream_ptr(dev)
+    # user -> movies (table order inside a user), then movie -> users (ascending rank) from the edges in that order
+    ucsr = csr_build(torch.stack([u, m]), None, num_nodes=max(num_users, num_items), device=dev, index=False)
+    urow = ucsr.row_ptr[:num_users + 1].contiguous()
+    R = ucsr.num_edges
+    rows = torch.repeat_interleave(torch.arange(num_users, device=dev), (urow[1:] - urow[:-1]))
+    pos = (torch.arange(R, device=dev) - urow[:-1][rows]).to(torch.int32)
+    # movie -> its (user, position) edges, users ascending: a stable sort of the user-CSR edges by movie.  The
+    # CSR is built over EDGE NUMBERS, which gives the permutation; user rank and position follow by lookup.
+    ecsr = csr_build(torch.stack([ucsr.col.to(torch.int64), torch.arange(R, device=dev)]), None,
+                     num_nodes=max(num_items, R, 1), device=dev, index=False)
+    irow = ecsr.row_ptr[:num_items + 1].contiguous()
+    perm = ecsr.col.to(torch.int64)
+    iusers = rows[perm].to(torch.int32).contiguous()
+    ipos = pos[perm].contiguous()
+    max_deg = int((urow[1:] - urow[:-1]).max().item()) if num_users else 1
+    bits_p = max(1, int(max_deg - 1).bit_length())
+    nblocks = 148 * 2
+    acc_cnt = torch.empty((nblocks, num_items), dtype=torch.int32, device=dev)
+    acc_first = torch.empty((nblocks, num_items), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    cap = max(1024, min(4 * R, 1 << 26))
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        pa = torch.empty(cap, dtype=torch.int32, device=dev)
+        pbb = torch.empty(cap, dtype=torch.int32, device=dev)
+        pc = torch.empty(cap, dtype=torch.int32, device=dev)
+        check(lib().pb200_cooc_pairs(ptr(urow), ptr(ucsr.col), ptr(irow), ptr(iusers), ptr(ipos), num_users, num_items,
+                                     int(threshold), bits_p, ptr(acc_cnt), ptr(acc_first), nblocks, ptr(keys), ptr(pa),
+                                     ptr(pbb), ptr(pc), cap, ptr(count), st), "cooc_pairs")
+        P = int(count.item())                      # build-time sync
+        if P <= cap:
+            break
+        cap = P
+    ei = torch.empty((2, 2 * P), dtype=torch.int64, device=dev)
+    ew = torch.empty(2 * P, dtype=torch.float32, device=dev)
+    if P:
+        ws_bytes = lib().pb200_cooc_edges_workspace_bytes(P)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib().pb200_cooc_edges(ptr(keys), ptr(pa), ptr(pbb), ptr(pc), P, ptr(ei), ptr(ew), ptr(ws), ws_bytes, st),
+              "cooc_edges")
+    return ei[0], ei[1], ew
+
+
 def count_topt(trace, num_neighbors):
     dev = N.device_of(trace)
     tr = N.dev_tensor(trace, torch.int32, dev)

@@ -127,11 +127,48 @@ class RandomWalkSampler:
                                      epoch, epoch_dev=epoch_dev, num_epochs=num_layers)
         return [NL.from_walk(ids[l], w[l], nv[l]) for l in range(num_layers)]
 
-    # ---- out of scope ------------------------------------------------------------------
-    def compute_ppr_matrix(self, *a, **k):
-        raise NotImplementedError("compute_ppr_matrix (reference :144-195) is outside the hot path "
-                                  "(SURVEY.md 8(f) N4); nothing in the reference calls it")
+    # ---- N4: PPR push variant ---------------------------------------------------
+    def _ppr_sources(self, nodes):
+        if isinstance(nodes, torch.Tensor):
+            nodes = nodes.tolist()
+        nodes = [int(v) for v in nodes]
+        # the reference sizes its vectors max(edge_index.max() + 1, max(nodes) + 1) and then indexes
+        # adj_list[source]: a source beyond the adjacency list raises IndexError (:176)
+        if nodes and (min(nodes) < 0 or max(nodes) >= self.csr.num_nodes):
+            raise IndexError("list index out of range")
+        return nodes
 
-    def precompute_top_neighbors(self, *a, **k):
-        raise NotImplementedError("precompute_top_neighbors (reference :197-229) is outside the hot "
-                                  "path (SURVEY.md 8(f) N4)")
+    def compute_ppr_dense(self, nodes, alpha=0.15, num_iterations=10):
+        """compute_ppr_matrix as a device tensor: float64 [len(nodes), num_nodes] (pb200_ppr_push)."""
+        return K.ppr_push(self.csr, self._ppr_sources(nodes), alpha, num_iterations)
+
+    def compute_ppr_matrix(self, nodes, alpha=0.15, num_iterations=10):
+        """reference :144-195 -- {(source, target): score} for every positive score, sources in the given
+        order, targets ascending (the reference's insertion order)."""
+        nodes = self._ppr_sources(nodes)
+        dense = K.ppr_push(self.csr, nodes, alpha, num_iterations).cpu().numpy()
+        ppr_matrix = {}
+        for row, source in zip(dense, nodes):
+            for target in row.nonzero()[0].tolist():
+                if row[target] > 0:
+                    ppr_matrix[(source, target)] = float(row[target])
+        return ppr_matrix
+
+    def precompute_top_neighbors(self, nodes, num_neighbors=10):
+        """reference :197-229 -- {source: (neighbors, weights)}: the num_neighbors largest PPR scores (ties by
+        smaller target id = the reference's stable reverse sort), weights normalised by their python-float sum."""
+        if isinstance(nodes, torch.Tensor):
+            nodes = nodes.tolist()
+        sources = self._ppr_sources(nodes)
+        dense = K.ppr_push(self.csr, sources, 0.15, 10)
+        ids, vals = K.topk_rows_f64(dense, num_neighbors)
+        ids, vals = ids.cpu().tolist(), vals.cpu().tolist()
+        top_neighbors = {}
+        for source, row_i, row_v in zip(nodes, ids, vals):
+            neighbors = [t for t in row_i if t >= 0]
+            weights = row_v[:len(neighbors)]
+            if weights:
+                total_weight = sum(weights)
+                weights = [w / total_weight for w in weights]
+            top_neighbors[source] = (neighbors, weights)
+        return top_neighbors
