@@ -14,6 +14,9 @@ T=10 neighbours.  One step = 2 x [walk/count/top-T kernel over all items] + fuse
   cpu_baseline   the oracle port (C walk sampler on all host threads + numpy forward) on a
                  bounded sample, rank 0 at N=1
 
+  c5         BASELINE configs[4] at --c5-scale (default 1/16: 625 k items, 250 M directed edges, 3 layers), graph
+             generated on the device: embeddings/s, walk roofline at DRAM scale, item-sharded exact top-10 with
+             the all-gather + merge, parity spot checks against the C oracle (bench_c5.run_c5)
   retrieval  BASELINE metric (2): all-item top-10 queries/s for exact / LSH / IVF search over C3-shaped
              embeddings (bench_search.run_retrieval): set B (spread) at every N, set A (the embeddings
              this run just computed from the reference checkpoint: collapsed) at N = 1
@@ -56,6 +59,8 @@ def parse():
     ap.add_argument("--precision", default="auto", choices=["fp32", "tf32", "auto"])
     ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the sharded step eagerly")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the retrieval (search) section")
+    ap.add_argument("--no-c5", action="store_true", help="skip the scaled C5 workload")
+    ap.add_argument("--c5-scale", type=float, default=1.0 / 16, help="C5 = 10 M items / 50 M users / 2 G ratings times this")
     return ap.parse_args()
 
 
@@ -405,6 +410,14 @@ def main_b200(args):
                                       "SURVEY fact 9)", cpu=False, iters=1, methods=("exact_ip", "exact_l2", "lsh_exhaustive", "ivf"))
                 retrieval["set_A"] = {k: ra[k] for k in ("embedding_set", "methods")}
                 retrieval["set_A"]["mean_pairwise_cosine_sample"] = float((emb_a[:2048] @ emb_a[:2048].t()).mean())
+    # ---- C5 (BASELINE.json configs[4]) at --c5-scale: device-generated graph, 3 layers, item-sharded search ----
+    c5 = None
+    if not args.no_c5:
+        import bench_c5 as BC
+        del flush
+        torch.cuda.empty_cache()
+        with contextlib.redirect_stdout(sys.stderr):
+            c5 = BC.run_c5(dev, scale=args.c5_scale)
     if rank != 0:
         if ws > 1:
             dist.destroy_process_group()
@@ -441,6 +454,8 @@ def main_b200(args):
             line["roofline"]["note"] = "rank 0's shard of the start nodes, kernel timed eagerly after the graph-replay region"
     if retrieval is not None:
         line["retrieval"] = retrieval
+    if c5 is not None:
+        line["c5"] = c5
     if ws == 1 and not args.no_cpu_baseline:
         r = run_cpu_port(inp, args.cpu_sample, 3, 1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")}
