@@ -173,7 +173,7 @@ def run_cpu_port(inp, sample, steps, warmup):
                 warmup_steps=warmup,
                 sample=f"{sample} of {inp['M']} start items per step (walks on the full graph, "
                        f"W=100 L=2 T=10, {inp['layers']} layers + forward on those rows); items/s "
-                       "extrapolates linearly; C walk port on all host threads + numpy fp32 forward",
+                       f"extrapolates linearly; C walk port ({cp['O'].C_BUILD}) on all host threads + numpy fp32 forward",
                 ms_per_step=dt * 1e3)
 
 

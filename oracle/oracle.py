@@ -3,15 +3,16 @@
 Plain numpy restatement of the reference's PinSage inference + retrieval hot
 path.  Only tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs may import this module; the
-product package must never do so (tests/test_no_oracle_on_product_path.py
-enforces it).
+product package must never do so
+(tests/test_abi_and_host.py::test_product_never_imports_the_oracle enforces it).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference).  Pinning status:
 
   S0-S3, P1-P5, G1-G4, E1 : PINNED by tests/golden/*.npz, which were produced by
       importing the unmodified reference in the build container
-      (tests/golden/make_golden.py).
+      (tests/golden/make_golden.py, make_golden_r2.py: incl. negative ids, the shipped
+      checkpoint, the unpatched sampler's visit distribution, and the 8(f) rows N1-N4).
   E2, L1, L2, I1, I2, B1  : PARITY UNPINNED.  The arithmetic lives in
       faiss-cpu==1.7.4 (requirements.txt:19), which is not vendored, not
       installed and not fetchable offline.  These functions restate faiss's
@@ -238,6 +239,7 @@ def count_topt_from_trace(trace, T):
 
 # ---- C restatement (oracle/walk_oracle.c) loader: fast path for big cases ----
 _C = None
+C_BUILD = None
 
 
 def c_oracle():
@@ -247,6 +249,20 @@ def c_oracle():
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} missing: run `make -C oracle` or __graft_entry__.build()")
+        # CPU baseline: -O3 -march=native, compiled on the machine that runs it (a .so built with
+        # -march=native elsewhere may not run here); the portable build is the fallback
+        global C_BUILD
+        C_BUILD = "-O3 (portable build)"
+        try:
+            import subprocess
+            import tempfile
+            out = os.path.join(tempfile.gettempdir(), f"liboracle_native_{os.getuid()}.so")
+            r = subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-pthread", "-std=c11", "-shared", "-o", out,
+                                os.path.join(_HERE, "walk_oracle.c")], capture_output=True, timeout=120)
+            if r.returncode == 0:
+                path, C_BUILD = out, "-O3 -march=native (built on this host)"
+        except Exception:        # noqa: BLE001 -- no compiler here: portable build
+            pass
         lib = ctypes.CDLL(path)
         lib.orc_walk_uniform53.restype = ctypes.c_uint64
         lib.orc_walk_uniform53.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,

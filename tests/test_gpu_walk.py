@@ -329,3 +329,40 @@ def test_multi_epoch_launch_equals_separate_calls(K, leaf):
             ref = s2.batch_sample_neighbors_tensor(starts, 10)
             for a, b in zip(layers[l].as_args()[:3], ref.as_args()[:3]):
                 np.testing.assert_array_equal(_np(a), _np(b))
+
+
+def test_integration_recipe_a_module_aliasing_runs_the_reference_imports():
+    """INTEGRATION.md recipe A, executed in a fresh interpreter: alias the mirror modules into sys.modules,
+    then use the REFERENCE's own import lines; the sampler obtained that way reproduces the reference golden."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import mre_b200
+for name in ("utils.random_walk", "utils.nearest_neighbors", "utils.evaluation", "model.pinsage", "model.layers",
+             "model.aggregators", "data.negative_sampler", "data.graph_builder"):
+    pkg = name.split(".")[0]
+    sys.modules.setdefault(pkg, __import__("mre_b200." + pkg, fromlist=["_"]))
+    sys.modules[name] = __import__("mre_b200." + name, fromlist=["_"])
+from utils.random_walk import RandomWalkSampler                      # reference inference.py:10
+from model.pinsage import PinSage                                     # reference inference.py:9
+from utils.nearest_neighbors import LSHIndex, WeakANDIndex            # reference inference.py:11
+from data.negative_sampler import NegativeSampler
+import numpy as np, torch
+from tests import helpers as Hh
+c = Hh.walk_case("walk_quant.npz")
+s = RandomWalkSampler(torch.from_numpy(c["ei"]), torch.from_numpy(c["w"]), walk_length=2, num_walks=100, seed=c["seed"])
+nbrs, wts = s.batch_sample_neighbors(c["starts"].tolist(), 10)
+for r in range(len(nbrs)):
+    nv = c["nvalid"][r]
+    assert nbrs[r] == c["ids"][r, :nv].tolist() and wts[r] == c["weights"][r, :nv].tolist()
+model = PinSage(16, 32, 16, 2).cuda().eval()
+emb = model.get_embeddings(torch.randn(120, 16), s, 10)
+assert emb.shape == (120, 16) and emb.device.type == "cpu"
+print("RECIPE_A_OK")
+''' % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and "RECIPE_A_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
