@@ -12,6 +12,6 @@ d = np.load("/tmp/c2_graph.npz")
 csr = K.csr_build(torch.from_numpy(d["ei"]), torch.from_numpy(d["w"]), num_nodes=int(d["N"]))
 nodes = torch.arange(62423, dtype=torch.int32, device="cuda")
 for e in range(4):
-    out = K.walk_topt(csr, nodes, 100, 2, 10, 1234, e)
+    out = K.walk_topt(csr, nodes, 100, 2, 10, 1234, 2 * e, num_epochs=2)      # one launch = both layers' samples (bench.py)
 torch.cuda.synchronize()
 print("ok", int(out[0].long().sum()))
