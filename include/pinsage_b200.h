@@ -413,6 +413,12 @@ int pb200_lsh_search_tables(const uint8_t* codes_q, int64_t nq, const uint8_t* c
                             const float* queries, const float* vectors, int dim, int k,
                             float* out_scores, int32_t* out_ids, int32_t* out_ncand,
                             pb200_stream_t stream);
+/* Same with a floor per query in output units (Hamming distance ascending, or dot score descending): passes for k > 32. */
+int pb200_lsh_search_tables_ex(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x, int64_t nx, int code_bytes,
+                               int num_tables, const int32_t* bucket_offsets, const int32_t* bucket_ids,
+                               const float* queries, const float* vectors, int dim, int k, const float* floor_scores,
+                               const int32_t* floor_ids, float* out_scores, int32_t* out_ids, int32_t* out_ncand,
+                               pb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * I1/I2  WeakANDIndex (utils/nearest_neighbors.py:70-139; faiss.IndexIVFFlat, L2)
@@ -432,6 +438,13 @@ int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* p
                      int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
                      const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
                      pb200_stream_t stream);
+/* pb200_ivf_search restricted to candidates strictly WORSE than (floor_dist[q], floor_ids[q]) under the
+ * (distance asc, id asc) order (NULL: no floor): k > 32 is served in passes of 32, each floored by the last
+ * result of the previous pass (faiss accepts any k). */
+int pb200_ivf_search_ex(const float* queries, int64_t nq, int dim, const int32_t* probes, int nprobe,
+                        const int32_t* list_offsets, const int32_t* list_ids, const float* list_vecs, int k,
+                        const float* floor_dist, const int32_t* floor_ids, float* out_dist, int32_t* out_ids,
+                        pb200_stream_t stream);
 
 /* Same results as pb200_ivf_search (bit for bit) on the tensor cores.  The caller prepares, once
  * per index, a padded list-ordered layout of the vectors (np rows, np % 128 == 0, every list

@@ -110,6 +110,10 @@ SIGNATURES = {
     "pb200_ivf_build": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                 c_size, c_ptr]),
     "pb200_ivf_centroid_update": (c_int, [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
+    "pb200_ivf_search_ex": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr,
+                                    c_ptr, c_ptr, c_ptr]),
+    "pb200_lsh_search_tables_ex": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                           c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "pb200_ivf_search": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int,
                                  c_ptr, c_ptr, c_ptr]),
 }

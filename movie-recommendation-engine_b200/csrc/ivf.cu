@@ -74,6 +74,9 @@ struct IvfSearchParams {
     // per-probe mode (few selected queries: one warp per (query, probe) instead of a 20-list
     // chain per warp); partial lists [slot][nprobe][32] are merged by topk_merge_kernel
     int per_probe; float* __restrict__ part_bad; int32_t* __restrict__ part_ids;
+    // optional floor per query (k > 32 in passes of 32): only candidates strictly worse than (floor_dist, floor_id)
+    // under the (distance, id) order are considered
+    const float* __restrict__ floor_dist; const int32_t* __restrict__ floor_id;
 };
 
 // One warp per query.  Each warp stages 32 list vectors at a time in shared memory with
@@ -96,6 +99,9 @@ __global__ void __launch_bounds__(128) ivf_search_kernel(const IvfSearchParams p
     const int pi1 = p.per_probe ? pi0 + 1 : p.nprobe;
     for (int c = lane; c < d; c += 32) qs[c] = p.q[qi * d + c];
     TopkLane e; e.bad = INFINITY; e.id = INT_MAX;
+    const bool floored = p.floor_dist != nullptr;
+    const float fl_b = floored ? p.floor_dist[qi] : 0.f;
+    const int fl_i = floored ? p.floor_id[qi] : 0;
     for (int pi = pi0; pi < pi1; ++pi) {
         const int l = p.probes[qi * p.nprobe + pi];
         if (l < 0) continue;  // warp-uniform
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(128) ivf_search_kernel(const IvfSearchParams p
                 for (int c = 0; c < d; ++c) { const float t = qs[c] - v[c]; dist = fmaf(t, t, dist); }
             }
             const int id = lane < cnt ? p.list_ids[base + lane] : -1;
-            topk_offer(e, dist, id, lane < cnt, p.k, lane);
+            topk_offer(e, dist, id, lane < cnt && (!floored || better(fl_b, fl_i, dist, id)), p.k, lane);
         }
     }
     if (p.per_probe) {
@@ -202,10 +208,12 @@ namespace pb200 {
 int ivf_search_run(const float* queries, int64_t nq, int dim, const int32_t* probes, int nprobe,
                    const int32_t* list_offsets, const int32_t* list_ids, const float* list_vecs, int k,
                    float* out_dist, int32_t* out_ids, const int32_t* qsel, const int32_t* qsel_count,
-                   int64_t qsel_base, float* part_bad, int32_t* part_ids, cudaStream_t stream) {
+                   int64_t qsel_base, float* part_bad, int32_t* part_ids, cudaStream_t stream,
+                   const float* floor_dist, const int32_t* floor_id) {
     const int per_probe = part_bad != nullptr;
     IvfSearchParams p{queries, nq, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k,
-                      out_dist, out_ids, qsel, qsel_count, qsel_base, per_probe, part_bad, part_ids};
+                      out_dist, out_ids, qsel, qsel_count, qsel_base, per_probe, part_bad, part_ids,
+                      floor_dist, floor_id};
     const int wpb = 4;
     const size_t smem = (size_t)wpb * (dim + 32 * (dim + 1)) * sizeof(float);
     if (smem > 200 * 1024) {
@@ -221,15 +229,24 @@ int ivf_search_run(const float* queries, int64_t nq, int dim, const int32_t* pro
 }
 }  // namespace pb200
 
-extern "C" int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* probes,
-                                int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
-                                const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
-                                pb200_stream_t stream) {
+extern "C" int pb200_ivf_search_ex(const float* queries, int64_t nq, int dim, const int32_t* probes,
+                                   int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
+                                   const float* list_vecs, int k, const float* floor_dist, const int32_t* floor_ids,
+                                   float* out_dist, int32_t* out_ids, pb200_stream_t stream) {
     PB_REQUIRE(nq >= 0 && dim > 0 && nprobe > 0, "ivf_search: bad sizes");
-    PB_REQUIRE(k > 0 && k <= 32, "ivf_search: k must be in [1, 32]");
+    PB_REQUIRE(k > 0 && k <= 32, "ivf_search: k must be in [1, 32] per pass (larger k: passes with a floor)");
+    PB_REQUIRE((floor_dist == nullptr) == (floor_ids == nullptr), "ivf_search: floor needs both distance and id");
     if (nq == 0) return PB200_OK;
     PB_REQUIRE(queries && probes && list_offsets && list_ids && list_vecs && out_dist && out_ids,
                "ivf_search: null pointer");
     return ivf_search_run(queries, nq, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k, out_dist,
-                          out_ids, nullptr, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+                          out_ids, nullptr, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream, floor_dist, floor_ids);
+}
+
+extern "C" int pb200_ivf_search(const float* queries, int64_t nq, int dim, const int32_t* probes,
+                                int nprobe, const int32_t* list_offsets, const int32_t* list_ids,
+                                const float* list_vecs, int k, float* out_dist, int32_t* out_ids,
+                                pb200_stream_t stream) {
+    return pb200_ivf_search_ex(queries, nq, dim, probes, nprobe, list_offsets, list_ids, list_vecs, k, nullptr, nullptr,
+                               out_dist, out_ids, stream);
 }

@@ -187,6 +187,8 @@ struct ProbeParams {
     const float* __restrict__ queries; const float* __restrict__ vectors; int d;
     int k;
     float* __restrict__ out_scores; int32_t* __restrict__ out_ids; int32_t* __restrict__ out_ncand;
+    // optional floor per query, in output units (Hamming distance, or dot score): k > 32 in passes of 32
+    const float* __restrict__ floor_score; const int32_t* __restrict__ floor_id;
 };
 
 // one warp per query; lane-per-candidate: one 32 B code (= one DRAM sector) per candidate
@@ -203,6 +205,9 @@ __global__ void __launch_bounds__(256) lsh_probe_kernel(const ProbeParams p) {
     const bool dot = p.vectors != nullptr;
     TopkLane e; e.bad = INFINITY; e.id = INT_MAX;
     int ncand = 0;
+    const bool floored = p.floor_score != nullptr;
+    const float fl_b = floored ? (dot ? -p.floor_score[qi] : p.floor_score[qi]) : 0.f;
+    const int fl_i = floored ? p.floor_id[qi] : 0;
     for (int t = 0; t < p.nt; ++t) {
         const uint32_t key = code_key(reinterpret_cast<const uint8_t*>(qc), t, p.key_bytes);
         const int b0 = p.offsets[(int64_t)t * (nb + 1) + key];
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(256) lsh_probe_kernel(const ProbeParams p) {
                 }
             }
             ncand += __popc(__ballot_sync(kFull, valid));
-            topk_offer(e, bad, id, valid, p.k, lane);
+            topk_offer(e, bad, id, valid && (!floored || better(fl_b, fl_i, bad, id)), p.k, lane);
         }
     }
     if (lane < p.k) {
@@ -351,18 +356,20 @@ extern "C" int pb200_lsh_build_tables(const uint8_t* codes_x, int64_t nx, int co
     return rc;
 }
 
-extern "C" int pb200_lsh_search_tables(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x,
-                                       int64_t nx, int code_bytes, int num_tables,
-                                       const int32_t* bucket_offsets, const int32_t* bucket_ids,
-                                       const float* queries, const float* vectors, int dim, int k,
-                                       float* out_scores, int32_t* out_ids, int32_t* out_ncand,
-                                       pb200_stream_t stream) {
+extern "C" int pb200_lsh_search_tables_ex(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x,
+                                          int64_t nx, int code_bytes, int num_tables,
+                                          const int32_t* bucket_offsets, const int32_t* bucket_ids,
+                                          const float* queries, const float* vectors, int dim, int k,
+                                          const float* floor_scores, const int32_t* floor_ids,
+                                          float* out_scores, int32_t* out_ids, int32_t* out_ncand,
+                                          pb200_stream_t stream) {
     const int kb = table_key_bytes(code_bytes, num_tables);
     if (!kb || code_bytes % 4) {
         set_error("lsh_search_tables: unsupported code/table geometry");
         return PB200_ERR_UNSUPPORTED;
     }
-    PB_REQUIRE(k > 0 && k <= 32, "lsh_search_tables: k must be in [1, 32]");
+    PB_REQUIRE(k > 0 && k <= 32, "lsh_search_tables: k must be in [1, 32] per pass (larger k: passes with a floor)");
+    PB_REQUIRE((floor_scores == nullptr) == (floor_ids == nullptr), "lsh_search_tables: floor needs both score and id");
     PB_REQUIRE((vectors == nullptr) == (queries == nullptr) && (!vectors || dim > 0),
                "lsh_search_tables: dot re-rank needs both queries and vectors");
     if (nq == 0) return PB200_OK;
@@ -373,7 +380,18 @@ extern "C" int pb200_lsh_search_tables(const uint8_t* codes_q, int64_t nq, const
     p.nt = num_tables; p.key_bytes = kb; p.offsets = bucket_offsets; p.bucket_ids = bucket_ids;
     p.queries = queries; p.vectors = vectors; p.d = dim; p.k = k;
     p.out_scores = out_scores; p.out_ids = out_ids; p.out_ncand = out_ncand;
+    p.floor_score = floor_scores; p.floor_id = floor_ids;
     const size_t smem = (size_t)8 * (code_bytes / 4) * 4;
     lsh_probe_kernel<<<(unsigned)ceil_div(nq, 8), 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("lsh_probe_kernel");
+}
+
+extern "C" int pb200_lsh_search_tables(const uint8_t* codes_q, int64_t nq, const uint8_t* codes_x,
+                                       int64_t nx, int code_bytes, int num_tables,
+                                       const int32_t* bucket_offsets, const int32_t* bucket_ids,
+                                       const float* queries, const float* vectors, int dim, int k,
+                                       float* out_scores, int32_t* out_ids, int32_t* out_ncand,
+                                       pb200_stream_t stream) {
+    return pb200_lsh_search_tables_ex(codes_q, nq, codes_x, nx, code_bytes, num_tables, bucket_offsets, bucket_ids, queries,
+                                      vectors, dim, k, nullptr, nullptr, out_scores, out_ids, out_ncand, stream);
 }

@@ -546,19 +546,46 @@ def lsh_build_tables(codes_x, num_tables):
     return offsets, bucket_ids
 
 
+def _passes_of_32(k, run_pass, nq, dev, worst):
+    """k results per query in passes of <= 32, each floored by the last result of the previous pass."""
+    scores = torch.full((nq, k), worst, dtype=torch.float32, device=dev)
+    ids = torch.full((nq, k), -1, dtype=torch.int32, device=dev)
+    floor_s = floor_i = None
+    extra = None
+    for lo in range(0, k, 32):
+        kk = min(32, k - lo)
+        s, i, extra_p = run_pass(kk, floor_s, floor_i)
+        if extra is None:
+            extra = extra_p
+        if floor_i is not None:                       # a query that was already short stays padded
+            dead = (floor_i < 0)[:, None]
+            s = torch.where(dead, torch.full_like(s, worst), s)
+            i = torch.where(dead, torch.full_like(i, -1), i)
+        scores[:, lo:lo + kk], ids[:, lo:lo + kk] = s, i
+        floor_s, floor_i = s[:, kk - 1].contiguous(), i[:, kk - 1].contiguous()
+    return scores, ids, extra
+
+
 def lsh_search_tables(codes_q, codes_x, num_tables, offsets, bucket_ids, k, queries=None,
                       vectors=None):
+    """Bucketed LSH search; any k (passes of 32 with a floor beyond that, like pb200_topk)."""
     dev = N.device_of(codes_x)
     nq, cb = codes_q.shape
-    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    ncand = torch.empty(nq, dtype=torch.int32, device=dev)
     d = 0 if vectors is None else vectors.size(1)
-    check(lib().pb200_lsh_search_tables(ptr(codes_q), nq, ptr(codes_x), codes_x.size(0), cb,
-                                        num_tables, ptr(offsets), ptr(bucket_ids), ptr(queries),
-                                        ptr(vectors), d, k, ptr(scores), ptr(ids), ptr(ncand),
-                                        stream_ptr(dev)), "lsh_search_tables")
-    return scores, ids, ncand
+    dot = vectors is not None
+
+    def run(kk, floor_s, floor_i):
+        scores = torch.empty((nq, kk), dtype=torch.float32, device=dev)
+        ids = torch.empty((nq, kk), dtype=torch.int32, device=dev)
+        ncand = torch.empty(nq, dtype=torch.int32, device=dev)
+        check(lib().pb200_lsh_search_tables_ex(ptr(codes_q), nq, ptr(codes_x), codes_x.size(0), cb,
+                                               num_tables, ptr(offsets), ptr(bucket_ids), ptr(queries),
+                                               ptr(vectors), d, kk, ptr(floor_s), ptr(floor_i), ptr(scores), ptr(ids),
+                                               ptr(ncand), stream_ptr(dev)), "lsh_search_tables")
+        return scores, ids, ncand
+    if k <= 32:
+        return run(k, None, None)
+    return _passes_of_32(k, run, nq, dev, float("-inf") if dot else float("inf"))
 
 
 def ivf_build(x, assign, nlist):
@@ -643,11 +670,17 @@ def ivf_search_tc_supported(nq, np_rows, d, k, nlist):
 
 
 def ivf_search(queries, probes, offsets, list_ids, list_vecs, k):
+    """IVF list scan; any k (passes of 32 with a floor beyond that)."""
     dev = N.device_of(list_vecs)
     nq, d = queries.shape
-    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    check(lib().pb200_ivf_search(ptr(queries), nq, d, ptr(probes), probes.size(1), ptr(offsets),
-                                 ptr(list_ids), ptr(list_vecs), k, ptr(dist), ptr(ids),
-                                 stream_ptr(dev)), "ivf_search")
-    return dist, ids
+
+    def run(kk, floor_s, floor_i):
+        dist = torch.empty((nq, kk), dtype=torch.float32, device=dev)
+        ids = torch.empty((nq, kk), dtype=torch.int32, device=dev)
+        check(lib().pb200_ivf_search_ex(ptr(queries), nq, d, ptr(probes), probes.size(1), ptr(offsets),
+                                        ptr(list_ids), ptr(list_vecs), kk, ptr(floor_s), ptr(floor_i), ptr(dist),
+                                        ptr(ids), stream_ptr(dev)), "ivf_search")
+        return dist, ids, None
+    if k <= 32:
+        return run(k, None, None)[:2]
+    return _passes_of_32(k, run, nq, dev, float("inf"))[:2]

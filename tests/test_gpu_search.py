@@ -425,3 +425,32 @@ def test_ivf_search_tensor_core_vs_oracle(K):
     rd, ri = O.ivf_search(x, cent, assign.cpu().numpy(), x[:nq], k, 20)
     np.testing.assert_allclose(dist.cpu().numpy(), rd, atol=2e-5)
     assert (ids.cpu().numpy() == ri).mean() > 0.98
+
+
+def test_ivf_and_lsh_tables_accept_k_above_32(K):
+    """faiss accepts any k; the list-scan and table-probe kernels hold 32 results per pass, larger k runs
+    in passes floored by the previous pass's last result under the (score, id) order."""
+    from mre_b200 import _native as N
+    from mre_b200.utils.nearest_neighbors import WeakANDIndex, LSHIndex
+    import mre_b200.synthetic as S
+    n, d, nlist, k = 5000, 32, 16, 75
+    x = S.spread_embeddings(n, d, seed=6, clusters=40, noise=0.3).numpy()
+    cent = O.kmeans(x, nlist, niter=4)
+    idx = WeakANDIndex(d, nlist, centroids=cent)
+    idx.build(x)
+    dist, ids = idx.search(x[:300], k=k)
+    rd, ri = O.ivf_search(x, cent, idx.assign.cpu().numpy(), x[:300], k, min(nlist, 20))
+    np.testing.assert_allclose(dist, rd, atol=2e-5)
+    assert (ids == ri).mean() > 0.98
+    assert np.all(np.diff(dist, axis=1)[np.isfinite(dist[:, 1:])] >= 0)
+    for rerank in ("hamming", "dot"):
+        lt = LSHIndex(d, 64, 8, mode="tables", rerank=rerank)
+        lt.build(x)
+        sc, li = lt.search(x[:200], k=k)
+        codes = lt.codes.cpu().numpy()
+        rs, rli, _nc = O.lsh_search_tables(codes, codes[:200], k, 8, vectors=x if rerank == "dot" else None,
+                                           queries=x[:200])
+        ok = rli >= 0
+        np.testing.assert_allclose(sc[ok], rs[ok], atol=2e-5)
+        assert (li == rli).mean() > 0.98 and ((li == -1) == (rli == -1)).all()
+        assert ok.sum(1).max() > 32                                   # the passes beyond the first were exercised
