@@ -82,7 +82,7 @@ def _build_bucket_index(csr):
 def build_walk_index(csr, leaf=None):
     """Adds a sampling index to a uint32-quanta CSR.  `leaf` (or PB200_WALK_LEAF): "auto" (bucket index
     when it applies, else the 8-ary tree with compact or wide leaves), "bucket", "compact", "wide"."""
-    if csr.cum_kind != 0 or csr.num_nodes == 0:
+    if csr.cum_kind != 0 or csr.num_nodes == 0 or csr.num_edges == 0:     # nothing to index: the flat kernel serves
         return csr
     import os
     want = (leaf or os.environ.get("PB200_WALK_LEAF", "auto")).lower()
@@ -210,8 +210,9 @@ def walk_topt(csr: CSR, starts, num_walks, walk_length, num_neighbors, seed, epo
               "walk_topt_indexed")
         return (ids, counts, weights, nvalid, trace) if return_trace else \
             (ids, counts, weights, nvalid)
-    check(lib().pb200_walk_topt(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cum) if csr.num_edges else
-                                ptr(csr.row_ptr), csr.cum_kind, csr.num_nodes, ptr(s), n,
+    # a graph without edges: col / cum are empty tensors (null pointers); every row is a dead end, nothing is read
+    check(lib().pb200_walk_topt(ptr(csr.row_ptr), ptr(csr.col) if csr.num_edges else ptr(csr.row_ptr),
+                                ptr(csr.cum) if csr.num_edges else ptr(csr.row_ptr), csr.cum_kind, csr.num_nodes, ptr(s), n,
                                 int(num_walks), int(walk_length), T, int(seed) & (2**64 - 1),
                                 int(epoch) & 0xFFFFFFFF, ptr(ids), ptr(counts), ptr(weights),
                                 ptr(nvalid), ptr(trace), stream_ptr(dev)), "walk_topt")
