@@ -1,6 +1,7 @@
 """Drop-in for the reference's ``model/layers.py``, B200-native (inference).
 
-GraphConvLayer (reference model/layers.py:5-77) collapses to ONE fused launch in eval mode:
+GraphConvLayer (reference model/layers.py:5-77) collapses to ONE fused launch in eval mode (training mode, with
+batch statistics, takes two launches and a column reduction: _forward_batch_stats):
     out = normalize(relu(BN_eval(linear_out([linear_self(x) | linear_neigh(neigh_x)]))))
       = normalize(relu([x | neigh_x] . W'^T + b'))
 with W' = diag(s) [W_o1 W_s | W_o2 W_n],  b' = s * (W_o1 b_s + W_o2 b_n + b_o - mean) + beta,
@@ -58,16 +59,36 @@ class GraphConvLayer(nn.Module):
         return hit[1], hit[2]
 
     def forward(self, x, neigh_x):
-        if self.training and x.size(0) > 1:
-            raise NotImplementedError(
-                "GraphConvLayer in training mode uses batch statistics (reference layers.py:68-69); "
-                "the B200 path is inference-only: call .eval()")
         dev = N.device_of(self.linear_self.weight)
         xd = N.dev_tensor(x, torch.float32, dev)
         nd = N.dev_tensor(neigh_x, torch.float32, dev)
+        if self.training and x.size(0) > 1:
+            out = self._forward_batch_stats(xd, nd)
+            return out if x.is_cuda else out.to(x.device)
         wf, bf = self._fold(with_bn=x.size(0) > 1)
         out = K.gather_dense(xd, wf, bf, a2=nd, flags=N.EPI_RELU | N.EPI_L2NORM)
         return out if x.is_cuda else out.to(x.device)
+
+    def _forward_batch_stats(self, xd, nd):
+        """Training mode (what a freshly constructed module is in, reference layers.py:68-69): BatchNorm1d
+        normalises with the statistics of THIS batch and moves its running statistics.  Two launches of the
+        exact-fp32 dense kernel around one column reduction: y = [x | neigh] W'^T + b' (BatchNorm not folded), then
+        out = normalize(relu(y * s + t)) as a diagonal GEMM with s = gamma / sqrt(var_batch + eps),
+        t = beta - mean_batch * s.  No gradients: this package is inference-only."""
+        wf, bf = self._fold(with_bn=False)
+        y = K.gather_dense(xd, wf, bf, a2=nd, flags=0)
+        var, mean = torch.var_mean(y, dim=0, unbiased=False)
+        bn = self.bn
+        with torch.no_grad():
+            if bn.track_running_stats and bn.running_mean is not None:
+                n = y.size(0)
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1 - m).add_(var * (n / (n - 1)), alpha=m)        # running_var is unbiased
+            s = bn.weight.detach() / torch.sqrt(var + bn.eps)
+            t = bn.bias.detach() - mean * s
+        return K.gather_dense(y, torch.diag(s).contiguous(), t.contiguous(), flags=N.EPI_RELU | N.EPI_L2NORM)
 
 
 def _pool(x, neighbors, weights, mode):

@@ -99,7 +99,7 @@ class LSHIndex:
         return _np_results(dist, ids)
 
 
-def train_kmeans(x, nlist, niter=20, seed=1234, max_points_per_centroid=256):
+def train_kmeans(x, nlist, niter=20, seed=1234, max_points_per_centroid=256, split_empty=True):
     """Lloyd iterations with faiss Clustering's defaults (subsample to 256 points/centroid,
     centroids initialised from a random subset, niter=20); assignment via pb200_topk (L2, k=1),
     update via the deterministic per-list mean kernel."""
@@ -116,7 +116,33 @@ def train_kmeans(x, nlist, niter=20, seed=1234, max_points_per_centroid=256):
         _, a = K.topk(x, cent, 1, N.METRIC_L2)
         offsets, _ids, vecs = K.ivf_build(x, a.view(-1).contiguous(), nlist)
         K.ivf_centroid_update(vecs, offsets, cent)
+        if split_empty:
+            _split_empty_clusters(cent, offsets, g)
     return cent
+
+
+def _split_empty_clusters(cent, offsets, gen, eps=1.0 / 1024):
+    """faiss Clustering::split_clusters: an empty cluster takes a copy of a donor cluster's centroid (donor drawn
+    with probability ~ size - 1), the two copies are nudged apart by (1 +- eps) on alternating coordinates and
+    share the donor's points from the next assignment on.  Same rule, this package's seeded generator instead of
+    faiss's (unpinned either way: faiss is absent).  Without it, near-duplicate (collapsed) embeddings leave
+    most lists dead for good.  nlist x d work: host-side bookkeeping of the build."""
+    sizes = (offsets[1:] - offsets[:-1]).to(torch.float64).cpu()
+    empty = (sizes == 0).nonzero().view(-1).tolist()
+    if not empty:
+        return 0
+    d = cent.size(1)
+    sign = torch.where(torch.arange(d, device=cent.device) % 2 == 0, 1.0 + eps, 1.0 - eps).to(cent.dtype)
+    for ci in empty:
+        p = (sizes - 1).clamp_min(0)
+        if float(p.sum()) <= 0:
+            break
+        cj = int(torch.multinomial(p, 1, generator=gen))
+        cent[ci] = cent[cj] * sign
+        cent[cj] = cent[cj] * (2.0 - sign)
+        sizes[ci] = sizes[cj] / 2
+        sizes[cj] -= sizes[ci]
+    return len(empty)
 
 
 class WeakANDIndex:

@@ -127,8 +127,6 @@ def test_graph_conv_layer_vs_reference_golden(dev):
     gx, gn = torch.from_numpy(g["gx"]).to(dev), torch.from_numpy(g["gn"]).to(dev)
     assert Hh.rel_row_err(layer(gx, gn).cpu().numpy(), g["g_out"]) < TOL
     assert Hh.rel_row_err(layer(gx[:1], gn[:1]).cpu().numpy(), g["g_out1"]) < TOL    # BN skipped
-    with pytest.raises(NotImplementedError):
-        layer.train()(gx, gn)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "auto"])
@@ -283,3 +281,26 @@ def test_reference_checkpoint_loads_and_matches_reference_outputs(dev):
         model.precision = prec
         assert Hh.rel_row_err(model(x).cpu().numpy(), g["emb_mlp"]) < TOL
         assert Hh.rel_row_err(model(x, None, nb, wt).cpu().numpy(), g["emb_imp"]) < TOL
+
+
+def test_graph_conv_layer_training_mode_matches_the_reference(dev):
+    """A freshly constructed reference GraphConvLayer is in TRAINING mode: batch statistics, running statistics
+    updated (momentum 0.1, unbiased variance), single-row batches skip BatchNorm.  Golden from the unmodified
+    reference (tests/golden/graphconv_train.npz)."""
+    from mre_b200.model.layers import GraphConvLayer
+    g = Hh.load("graphconv_train.npz")
+    layer = GraphConvLayer(20, 12)
+    layer.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd0.")})
+    layer = layer.to(dev)
+    assert layer.training
+    gx, gn = torch.from_numpy(g["gx"]).to(dev), torch.from_numpy(g["gn"]).to(dev)
+    assert Hh.rel_row_err(layer(gx, gn).cpu().numpy(), g["out1"]) < 1e-4
+    assert Hh.rel_row_err(layer(gx * 0.5, gn + 1.0).cpu().numpy(), g["out2"]) < 1e-4
+    assert Hh.rel_row_err(layer(gx[:1], gn[:1]).cpu().numpy(), g["out_single"]) < 1e-4
+    sd = layer.state_dict()
+    for k in ("bn.running_mean", "bn.running_var"):
+        np.testing.assert_allclose(sd[k].cpu().numpy(), g["sd1." + k], rtol=1e-4, atol=1e-6)
+    assert int(sd["bn.num_batches_tracked"]) == int(g["sd1.bn.num_batches_tracked"]) == 2
+    layer.eval()                                                   # eval afterwards uses the moved running statistics
+    out_eval = layer(gx, gn)
+    assert out_eval.shape == (33, 12)

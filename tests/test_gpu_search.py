@@ -454,3 +454,32 @@ def test_ivf_and_lsh_tables_accept_k_above_32(K):
         np.testing.assert_allclose(sc[ok], rs[ok], atol=2e-5)
         assert (li == rli).mean() > 0.98 and ((li == -1) == (rli == -1)).all()
         assert ok.sum(1).max() > 32                                   # the passes beyond the first were exercised
+
+
+def test_kmeans_resplits_empty_clusters_on_collapsed_data(K):
+    """on near-duplicate embeddings plain Lloyd leaves lists empty for good (an empty list kept its
+    stale centroid); with faiss's split rule empty lists are re-seeded from populated ones."""
+    from mre_b200.utils.nearest_neighbors import train_kmeans
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1, 32, generator=g)
+    x = torch.nn.functional.normalize(base + 0.01 * torch.randn(4000, 32, generator=g), dim=1)
+    x[:1000] = x[0]                                               # a quarter of the points are exact duplicates
+    x = x.cuda()
+    init_dupes = x[:64].clone()                                   # 64 identical initial centroids: 63 lists start empty
+
+    def used(split):
+        import mre_b200.utils.nearest_neighbors as NN
+        cent = init_dupes.clone()
+        for _ in range(12):
+            _, a = K.topk(x, cent, 1, 1)
+            offsets, _ids, vecs = K.ivf_build(x, a.view(-1).contiguous(), 64)
+            K.ivf_centroid_update(vecs, offsets, cent)
+            if split:
+                NN._split_empty_clusters(cent, offsets, torch.Generator().manual_seed(1))
+        _, a = K.topk(x, cent, 1, 1)
+        assert torch.isfinite(cent).all()
+        return torch.unique(a).numel()
+    without, with_split = used(False), used(True)
+    assert without <= 8 and with_split >= 16 and with_split > without, (without, with_split)
+    cent = train_kmeans(x, 64, niter=10)                          # the public entry point runs with the split
+    assert torch.isfinite(cent).all() and torch.unique(K.topk(x, cent, 1, 1)[1]).numel() >= 16
