@@ -50,6 +50,7 @@ struct SearchParams {
     int ks;                          // shortlist length (16 or 32)
     int splits; int64_t split_len;   // item chunks per query group; chunk length (multiple of kTileN)
     int stages, align_slack;
+    int scan_append;                 // 1: append + periodic warp-sort prune (ks = 16); 0: sorted insertion per candidate
     int kind;                        // 0: tf32 operands (32 per 128 B chunk row), 1: bf16 (64 per chunk row)
     const float* __restrict__ hx;    // 0.5 |x|^2, padded to a multiple of 128 items (L2 only)
     // IVF (pb200_ivf_search_tc): items are list ordered, every list padded to whole 128-item tiles;
@@ -119,6 +120,62 @@ __device__ __noinline__ float insert_column(unsigned m, float fi, uint32_t klo, 
     return thr;
 }
 
+// ---- scan mode 1: append + prune (ks = 16) ----
+// A row (= one lane) APPENDS every candidate that beats its threshold to its own buffer -- a predicated
+// store and an increment, no cross-lane traffic, eight independent appends per 8-column group instead of a
+// ~45-instruction dependent chain per insertion -- and the threshold is only refreshed when a buffer is
+// about to overflow: the warp then sorts that row's <= 30 keys (bitonic network over the lanes), keeps the
+// best 16 and reads the new threshold off rank 15.  The shortlist is still exactly the ks best TF32 scores of
+// the scanned columns: a key that belongs to the final top-ks beat every earlier (laxer) threshold, so it was
+// appended, and a prune only drops keys that 16 better ones dominate.
+constexpr int kScanCap = 30;          // keys per row buffer (lanes 30, 31 of the sort hold "empty")
+constexpr int kScanStride = 31;       // odd row stride (in keys): the per-lane appends spread over the banks
+constexpr int kScanTrig = kScanCap - 8;   // a group appends <= 8 keys per row: prune above this fill
+
+// Bitonic sort (descending) of one key per lane.
+__device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(kFull, key, j);
+            const bool take_max = ((lane & k) == 0) == ((lane & j) == 0);     // k == 32: descending everywhere
+            const bool gt = key > other;
+            key = (gt == take_max) ? key : other;
+        }
+    }
+    return key;
+}
+
+// Prunes every row of the warp whose fill exceeds `trig` (trig < 0: every non-empty row): the warp sorts the
+// row's keys, keeps the best ks and reads the new threshold off rank ks - 1.  Returns the lane's updated
+// threshold; `cnt` is the lane's own fill.
+// Measured alternatives (C3, cycles of one scan warp, make EXTRA=-DPB200_SEARCH_PROFILE): this form spends 2.0 M
+// of 7.2 M cycles in prunes (~1,100 per row: a dependent chain of 30 shuffles); four rows per pass with
+// interleaved chains + pruning every row above a lower fill: ~700 per row but 1.6 x the rows, same 2.0 M, and the
+// longer stalls of one warp made the other scan warps wait for the accumulator (exact search 4.53 -> 5.14 ms);
+// every lane folding its own pending keys into its sorted prefix by insertion (all 32 rows per event): 13 k
+// cycles per event, 1.7 M in total (5.05 ms).  The pending buffers cost the third ring stage (shared memory),
+// which is what bounds this mode now: the scan warps wait 19 % of their time for the next accumulator.
+__device__ __noinline__ float scan_prune(unsigned long long* wl, int& cnt, float thr, int ks, int lane, int trig) {
+    unsigned need = __ballot_sync(kFull, cnt > trig && cnt > 0);
+    while (need) {
+        const int r = __ffs(need) - 1;
+        need &= need - 1;
+        const int c_r = __shfl_sync(kFull, cnt, r);
+        unsigned long long key = lane < c_r ? wl[r * kScanStride + lane] : 0ull;
+        key = warp_sort_desc(key, lane);
+        if (lane < ks) wl[r * kScanStride + lane] = key;
+        const uint32_t last = __shfl_sync(kFull, (uint32_t)(key >> 32), ks - 1);    // 0: fewer than ks keys so far
+        if (lane == r) {
+            cnt = c_r < ks ? c_r : ks;
+            if (last) thr = ord2f(last);
+        }
+    }
+    __syncwarp();
+    return thr;
+}
+
 template <int kMetric>
 __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchParams p,
                                                                 const __grid_constant__ CUtensorMap tm_q,
@@ -136,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
     const uint32_t b_base = sbase + (uint32_t)(qt * nchunks) * kABytes;  // [S] 16 KB tiles
     uint8_t* tail = smem + (size_t)(qt * nchunks) * kABytes + (size_t)S * kNBytes;
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(tail);   // [qt * 128][ks] sorted, 0 = empty
-    const size_t list_bytes = (size_t)p.ks * qt * kTileM * 8;
+    const size_t list_bytes = (size_t)(p.scan_append ? kScanStride : p.ks) * qt * kTileM * 8;
     const uint32_t bars = smem_u32(tail + list_bytes);
     auto bar = [&](int slot) { return bars + 8u * (uint32_t)slot; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + list_bytes + kNumBars * 8);
@@ -267,7 +324,9 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
         const int qi = e >> 2, quarter = warp & 3;           // TMEM lane quarter = warp % 4
         const int row0 = qi * kTileM + quarter * 32;         // this warp's 32 rows of the CTA
         const int ks = p.ks;
-        unsigned long long* wl = lists + (size_t)row0 * ks;  // row r of the warp: wl[r * ks + rank]
+        const bool append = p.scan_append != 0;
+        // row r of the warp: wl[r * ks + rank] (sorted), or wl[r * kScanStride + i] (append buffer)
+        unsigned long long* wl = lists + (size_t)row0 * (append ? kScanStride : ks);
         int tc_ = 0;
         long long sp_wait = 0, sp_ld = 0, sp_fast = 0, sp_slow = 0, sp_groups = 0, sp_slowg = 0, sp_t0 = SP_NOW();
         long long sp_late_slow = 0, sp_late_slowg = 0, sp_late_cand = 0, sp_late_votes = 0, sp_cand = 0;
@@ -279,8 +338,9 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
             const int n_begin = (int)sg.n_begin, n_end = (int)sg.n_end;
             const int64_t q = qg * rows_per_cta + row0 + lane;
             const bool row_ok = q < p.nq;
-            for (int i = lane; i < 32 * ks; i += 32) wl[i] = 0ull;
+            if (!append) for (int i = lane; i < 32 * ks; i += 32) wl[i] = 0ull;
             __syncwarp();
+            int cnt = 0;                                    // append mode: keys in this row's buffer
             float thr = row_ok ? -INFINITY : INFINITY;      // score of rank ks-1 once the list is full
             uint4 pm = make_uint4(0u, 0u, 0u, 0u);
             if (p.pmask && row_ok) pm = __ldg(reinterpret_cast<const uint4*>(p.pmask) + q);
@@ -329,7 +389,27 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
                         const bool slowp = __any_sync(kFull, gm >= thr_t);
                         SP_ADD(sp_fast, g0);
                         sp_groups += 1;
-                        if (slowp) {
+                        if (slowp && append) {
+                            const long long s0 = SP_NOW();
+                            sp_slowg += 1;
+                            unsigned long long* mine = wl + lane * kScanStride;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (f[i] >= thr_t && col0 + g * 8 + i < n_end) {
+                                    mine[cnt] = make_key(f[i], (uint32_t)(col0 + g * 8 + i));
+                                    ++cnt;
+                                }
+                            }
+                            if (__any_sync(kFull, cnt > kScanTrig)) {
+                                const long long p0 = SP_NOW();
+                                __syncwarp();
+                                thr = scan_prune(wl, cnt, thr, ks, lane, kScanTrig);
+                                thr_t = elig ? thr : INFINITY;
+                                SP_ADD(sp_late_votes, p0);                                   // cycles in prunes
+                                sp_late_slowg += 1;                                          // prune events
+                            }
+                            SP_ADD(sp_slow, s0);
+                        } else if (slowp) {
                             const long long s0 = SP_NOW();
                             sp_slowg += 1;
                             // all 8 votes first, against the threshold at the start of the group: a vote
@@ -374,10 +454,21 @@ __global__ void __launch_bounds__(kThreads, 1) search_tc_kernel(const SearchPara
 #endif
             // segment done: every row's sorted list -> short_keys[sp][q][0..ks)
             __syncwarp();
-            for (int r = 0; r < 32; ++r) {
-                const int64_t qr = qg * rows_per_cta + row0 + r;
-                if (qr >= p.nq) break;
-                if (lane < ks) p.short_keys[((size_t)sp * p.nq + qr) * ks + lane] = wl[r * ks + lane];
+            if (append) {
+                thr = scan_prune(wl, cnt, thr, ks, lane, -1);       // sort what is left in every buffer
+                for (int r = 0; r < 32; ++r) {
+                    const int64_t qr = qg * rows_per_cta + row0 + r;
+                    if (qr >= p.nq) break;
+                    const int c_r = __shfl_sync(kFull, cnt, r);
+                    if (lane < ks)
+                        p.short_keys[((size_t)sp * p.nq + qr) * ks + lane] = lane < c_r ? wl[r * kScanStride + lane] : 0ull;
+                }
+            } else {
+                for (int r = 0; r < 32; ++r) {
+                    const int64_t qr = qg * rows_per_cta + row0 + r;
+                    if (qr >= p.nq) break;
+                    if (lane < ks) p.short_keys[((size_t)sp * p.nq + qr) * ks + lane] = wl[r * ks + lane];
+                }
             }
             __syncwarp();
         }
@@ -556,6 +647,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
 // ---- host side ----
 struct Plan {
     int qt = 0, nchunks = 0, ks = 0, splits = 0, stages = 0, grid = 0, fsplits = 0, fsplits0 = 0, align_slack = 1024;
+    int scan_append = 0;
     int64_t split_len, nx_pad, cap_f, cap_f0;
     size_t smem_bytes;
     // workspace offsets
@@ -575,10 +667,14 @@ static bool make_geometry(int64_t nq, int64_t nx, Plan& p) {
     // was measured slower, 4.99 vs 4.28 ms at C3, and removed.)
     p.align_slack = 1024;
     auto fixed_bytes = [&](int qt) {
-        return (size_t)qt * p.nchunks * kABytes + (size_t)p.ks * qt * kTileM * 8 + kNumBars * 8 + 16;
+        return (size_t)qt * p.nchunks * kABytes + (size_t)(p.scan_append ? kScanStride : p.ks) * qt * kTileM * 8 +
+               kNumBars * 8 + 16;
     };
     const size_t budget = 225 * 1024;
-    p.qt = (nq > 128 && fixed_bytes(2) + 1024 + 3 * (size_t)kNBytes <= budget) ? 2 : 1;
+    // append-mode buffers are twice the sorted lists: two ring stages are enough there (the scan, not the
+    // item stream, sets the pace: tensor pipe 20-25 % busy), the sorted-insertion mode keeps >= 3
+    const int min_stages2 = p.scan_append ? 2 : 3;
+    p.qt = (nq > 128 && fixed_bytes(2) + 1024 + min_stages2 * (size_t)kNBytes <= budget) ? 2 : 1;
     const size_t fixed = fixed_bytes(p.qt) + p.align_slack;
     if (fixed + 2 * (size_t)kNBytes > budget) return false;
     int st = (int)((budget - fixed) / kNBytes);
@@ -609,6 +705,7 @@ static bool make_plan(int64_t nq, int64_t nx, int dim, int k, bool has_exclude, 
     const int ks_env = env_int("PB200_TOPK_TC_KS", 0);
     if (ks_env == 16 || ks_env == 32) { if (ks_env >= need) p.ks = ks_env; }
     p.nchunks = (dim + kChunkK - 1) / kChunkK;
+    p.scan_append = (p.ks == 16 && env_int("PB200_TOPK_TC_SCAN", 1) != 0) ? 1 : 0;
     if (!make_geometry(nq, nx, p)) return false;
     p.nx_pad = ceil_div(nx, kTileN) * kTileN + kTileN;
     // fp32 re-runs: a first round for up to 1,024 uncertified queries with many item splits (the
@@ -714,7 +811,7 @@ extern "C" int pb200_topk_tc(const float* queries, int64_t nq, const float* item
     }
     tcs::SearchParams sp{};
     sp.nq = nq; sp.nx = nx; sp.d = dim; sp.nchunks = pl.nchunks; sp.qt = pl.qt; sp.ks = pl.ks;
-    sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack; sp.kind = 0;
+    sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack; sp.kind = 0; sp.scan_append = pl.scan_append;
     sp.hx = hx;
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + pl.off_short);
     // slots no segment starts at stay empty (0)
@@ -816,6 +913,7 @@ static bool make_hplan(int64_t nq, int64_t nx, int code_bytes, int k, bool share
     if (code_bytes <= 0 || nbits > 512 || k <= 0 || k > 32 || nq <= 0 || nx <= 0) return false;
     HPlan h{};
     h.g.ks = k <= 16 ? 16 : 32;
+    h.g.scan_append = (h.g.ks == 16 && env_int("PB200_TOPK_TC_SCAN", 1) != 0) ? 1 : 0;
     h.g.nchunks = (nbits + 63) / 64;
     if (!make_geometry(nq, nx, h.g)) return false;
     h.shared = shared;
@@ -891,6 +989,7 @@ extern "C" int pb200_hamming_topk_tc(const uint8_t* codes_q, int64_t nq, const u
     tcs::SearchParams sp{};
     sp.nq = nq; sp.nx = nx; sp.d = nbits; sp.nchunks = pl.nchunks; sp.qt = pl.qt; sp.ks = pl.ks;
     sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack;
+    sp.scan_append = pl.scan_append;
     sp.kind = 1; sp.hx = nullptr;
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + h.off_short);
     PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
@@ -935,6 +1034,7 @@ static bool make_iplan(int64_t nq, int64_t np, int dim, int k, int nlist, int np
         return false;
     IPlan h{};
     h.g.ks = k <= 12 ? 16 : 32;
+    h.g.scan_append = (h.g.ks == 16 && env_int("PB200_TOPK_TC_SCAN", 1) != 0) ? 1 : 0;
     h.g.nchunks = (dim + kChunkK - 1) / kChunkK;
     if (!make_geometry(nq, np, h.g)) return false;
     size_t off = 0;
@@ -1021,6 +1121,7 @@ extern "C" int pb200_ivf_search_tc(const float* queries, int64_t nq, int dim, co
     tcs::SearchParams sp{};
     sp.nq = nq; sp.nx = np; sp.d = dim; sp.nchunks = pl.nchunks; sp.qt = pl.qt; sp.ks = pl.ks;
     sp.splits = pl.splits; sp.split_len = pl.split_len; sp.stages = pl.stages; sp.align_slack = pl.align_slack;
+    sp.scan_append = pl.scan_append;
     sp.kind = 0; sp.hx = hxp; sp.tile_list = tile_list; sp.pmask = reinterpret_cast<const uint32_t*>(pmask);
     sp.short_keys = reinterpret_cast<unsigned long long*>(ws + h.off_short);
     PB_CUDA(cudaMemsetAsync(sp.short_keys, 0, (size_t)pl.splits * nq * pl.ks * 8, stream));
