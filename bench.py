@@ -14,7 +14,8 @@ T=10 neighbours.  One step = 2 x [walk/count/top-T kernel over all items] + fuse
   cpu_baseline   the oracle port (C walk sampler on all host threads + numpy forward) on a
                  bounded sample, rank 0 at N=1
 
-  c5         BASELINE configs[4] at --c5-scale (default 1/16: 625 k items, 250 M directed edges, 3 layers), graph
+  c5         BASELINE configs[4] at --c5-scale (default 1/16 on 1-2 GPUs: 625 k items, 250 M directed edges, 3 layers;
+             1/8 on 4-8 GPUs: 1.25 M items, 500 M directed edges), graph
              generated on the device: embeddings/s, walk roofline at DRAM scale, item-sharded exact top-10 with
              the all-gather + merge, parity spot checks against the C oracle (bench_c5.run_c5)
   retrieval  BASELINE metric (2): all-item top-10 queries/s for exact / LSH / IVF search over C3-shaped
@@ -60,7 +61,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the sharded step eagerly")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the retrieval (search) section")
     ap.add_argument("--no-c5", action="store_true", help="skip the scaled C5 workload")
-    ap.add_argument("--c5-scale", type=float, default=1.0 / 16, help="C5 = 10 M items / 50 M users / 2 G ratings times this")
+    ap.add_argument("--c5-scale", type=float, default=None,
+                    help="C5 = 10 M items / 50 M users / 2 G ratings times this (default: 1/16 on 1-2 GPUs, 1/8 on 4-8)")
     return ap.parse_args()
 
 
@@ -417,7 +419,7 @@ def main_b200(args):
         del flush
         torch.cuda.empty_cache()
         with contextlib.redirect_stdout(sys.stderr):
-            c5 = BC.run_c5(dev, scale=args.c5_scale)
+            c5 = BC.run_c5(dev, scale=args.c5_scale if args.c5_scale else (1.0 / 16 if ws <= 2 else 1.0 / 8))
     if rank != 0:
         if ws > 1:
             dist.destroy_process_group()
