@@ -846,11 +846,11 @@ static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
 #undef PB_BB
 #undef PB_BK
     }
-#define PB_B3(L_, T_, V_) do { if (minb == 7) return launch_bucket_variant<L_, T_, V_, 7>(p, pk, stream); \
-                               if (minb == 8) return launch_bucket_variant<L_, T_, V_, 8>(p, pk, stream); \
+    // one walk per lane (PB200_WALK_BATCH=0): the stages measured on the way, kept selectable for tools/tune_walk.py --
+    // 0 = first working version, 13 = lean probe loop + shared-memory select, 213 = 13 + ld.global.cg, at 6 or 8 blocks / SM
+#define PB_B3(L_, T_, V_) do { if (minb == 8) return launch_bucket_variant<L_, T_, V_, 8>(p, pk, stream); \
                                return launch_bucket_variant<L_, T_, V_, 6>(p, pk, stream); } while (0)
-#define PB_B(L_, T_) do { if (var == 13) PB_B3(L_, T_, 13); if (var == 113) PB_B3(L_, T_, 113); if (var == 213) PB_B3(L_, T_, 213); \
-                          if (var == 313) PB_B3(L_, T_, 313); PB_B3(L_, T_, 0); } while (0)
+#define PB_B(L_, T_) do { if (var == 13) PB_B3(L_, T_, 13); if (var == 213) PB_B3(L_, T_, 213); PB_B3(L_, T_, 0); } while (0)
     if (p.trace_out) { if (p.L == 2) PB_B(2, true); PB_B(0, true); }
     if (p.L == 2) PB_B(2, false);
     PB_B(0, false);
