@@ -437,7 +437,7 @@ def main_b200(args):
                            exchange=os.environ.get("PB200_SHARD_EXCHANGE", "p2p") + " (neighbour rows of h read from peer memory)" if ws > 1 else "none",
                            csr_build_s=round(csr_s, 3), graph_gen_s=round(inp["gen_s"], 1),
                            csr_bytes=sampler.csr.nbytes(), walk_index_bytes=sampler.csr.index_nbytes(),
-                           walk_index="bucket" if sampler.csr.leaf_format == N.LEAF_BUCKET else "tree",
+                           walk_index={N.LEAF_BUCKET: "bucket", N.LEAF_BUCKET32: "bucket32"}.get(sampler.csr.leaf_format, "tree"),
                            wall_s_timed_region=round(wall_dev, 4)),
             "e2e": {"value": M * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": inp["x"].numel() * 4, "d2h_bytes_per_step": M * inp["E"] * 4,

@@ -136,6 +136,16 @@ int pb200_walk_bucket_plan(const int64_t* row_ptr, const void* cum, int64_t num_
 int pb200_walk_bucket_fill(const int64_t* row_ptr, const int32_t* col, const void* cum,
                            int64_t num_nodes, const void* workspace, uint32_t* meta, uint32_t* leaf,
                            uint64_t total_buckets, pb200_stream_t stream);
+/* BUCKET32: the bucket format for graphs with more than 2^24 nodes -- SIX slots per 32-byte block {6 x u8 rel,
+ * 2 unused bytes (128), 6 x u32 neighbour id}; the shift rule then forbids 7 edges per bucket.  The _ex entry
+ * points take the format (PB200_LEAF_BUCKET or PB200_LEAF_BUCKET32). */
+#define PB200_LEAF_BUCKET32 3
+int pb200_walk_bucket_plan_ex(const int64_t* row_ptr, const void* cum, int64_t num_nodes, uint32_t* meta,
+                              uint64_t* info_out, void* workspace, size_t workspace_bytes, int leaf_format,
+                              pb200_stream_t stream);
+int pb200_walk_bucket_fill_ex(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                              int64_t num_nodes, const void* workspace, uint32_t* meta, uint32_t* leaf,
+                              uint64_t total_buckets, int leaf_format, pb200_stream_t stream);
 /* max over all 8-edge leaf blocks of (last - first cumulative weight) -> *max_range_out (device u32) */
 int pb200_walk_index_leaf_range(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
                                 uint32_t* max_range_out, pb200_stream_t stream);

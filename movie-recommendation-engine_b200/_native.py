@@ -45,6 +45,8 @@ SIGNATURES = {
     "pb200_walk_bucket_workspace_bytes": (c_size, [c_i64]),
     "pb200_walk_bucket_plan": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "pb200_walk_bucket_fill": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_u64, c_ptr]),
+    "pb200_walk_bucket_plan_ex": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_int, c_ptr]),
+    "pb200_walk_bucket_fill_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_u64, c_int, c_ptr]),
     "pb200_walk_topt_indexed_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_int,
                                            c_int, c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                            c_ptr]),
@@ -125,7 +127,7 @@ PREC_FP32, PREC_TF32, PREC_AUTO = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "auto": PREC_AUTO}
 METRIC_IP, METRIC_L2 = 0, 1
 SHARD_BLOCKS, SHARD_CYCLIC = 0, 1
-LEAF_WIDE, LEAF_COMPACT, LEAF_BUCKET = 0, 1, 2          # sampling-index leaf formats (pb200_walk_index_build_ex)
+LEAF_WIDE, LEAF_COMPACT, LEAF_BUCKET, LEAF_BUCKET32 = 0, 1, 2, 3          # sampling-index leaf formats (pb200_walk_index_build_ex)
 
 _lib = None
 

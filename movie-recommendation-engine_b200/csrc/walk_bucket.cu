@@ -19,6 +19,8 @@
 //   (utils/random_walk.py:72-79).  The edge containing t overlaps the bucket containing t, so
 //   it is always present.
 //
+//   PB200_LEAF_BUCKET32 (graphs with more than 2^24 nodes): the same with SIX slots per block --
+//       bytes 0..5 rel_i, bytes 6..7 unused (128), bytes 8..31 six 32-bit neighbour ids.
 //   s = the largest shift (<= 7) for which no bucket is overlapped by 9 edges: edges i..i+8
 //   share a bucket iff (cum_i - 1) >> s == cum_{i+7} >> s, so
 //   s = min(7, min_i msb((cum_i - 1) xor cum_{i+7})).  Needs every weight >= 1 quantum and node
@@ -31,6 +33,7 @@
 namespace pb200 {
 
 // one warp per row: shift, bucket count, zero-weight detection
+template <int kSlots>
 __global__ void __launch_bounds__(256) wbkt_plan_kernel(const int64_t* __restrict__ row_ptr,
                                                         const uint32_t* __restrict__ cum, int64_t N,
                                                         uint4* meta, unsigned long long* cnt,
@@ -48,9 +51,9 @@ __global__ void __launch_bounds__(256) wbkt_plan_kernel(const int64_t* __restric
             const uint32_t b = cum[r0 + i];
             const uint32_t a = i ? cum[r0 + i - 1] : 0u;
             if (b == a) { ++zeros; continue; }
-            if (i + 8 < deg) {
-                const uint32_t x = (b - 1u) ^ cum[r0 + i + 7];
-                smin = min(smin, 31 - __clz((int)x));       // x != 0: cum[i+7] >= b > b - 1
+            if (i + kSlots < deg) {                          // edges i .. i + kSlots must not share a bucket
+                const uint32_t x = (b - 1u) ^ cum[r0 + i + kSlots - 1];
+                smin = min(smin, 31 - __clz((int)x));       // x != 0: cum[i + kSlots - 1] >= b > b - 1
             }
         }
         smin = __reduce_min_sync(kFull, smin);
@@ -68,6 +71,7 @@ __global__ void wbkt_total_kernel(const unsigned long long* off, int64_t N, unsi
 }
 
 // one thread per bucket
+template <int kSlots>
 __global__ void __launch_bounds__(256) wbkt_fill_kernel(const int64_t* __restrict__ row_ptr,
                                                         const int32_t* __restrict__ col,
                                                         const uint32_t* __restrict__ cum, int64_t N,
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(256) wbkt_fill_kernel(const int64_t* __restric
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t e = a + q;
-            bool valid = e < deg;
+            bool valid = q < kSlots && e < deg;
             if (valid && q) valid = (uint64_t)cum[r0 + e - 1] < base + w;   // starts inside the bucket
             if (valid) {
                 const uint64_t d = (uint64_t)cum[r0 + e] - base;
@@ -113,13 +117,18 @@ __global__ void __launch_bounds__(256) wbkt_fill_kernel(const int64_t* __restric
         uint32_t o[8];
         o[0] = rel[0] | (rel[1] << 8) | (rel[2] << 16) | (rel[3] << 24);
         o[1] = rel[4] | (rel[5] << 8) | (rel[6] << 16) | (rel[7] << 24);
+        if (kSlots == 6) {
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-            const int sh = 8 * pl;
-            o[2 + 2 * pl] = ((id[0] >> sh) & 255u) | (((id[1] >> sh) & 255u) << 8) |
-                            (((id[2] >> sh) & 255u) << 16) | (((id[3] >> sh) & 255u) << 24);
-            o[3 + 2 * pl] = ((id[4] >> sh) & 255u) | (((id[5] >> sh) & 255u) << 8) |
-                            (((id[6] >> sh) & 255u) << 16) | (((id[7] >> sh) & 255u) << 24);
+            for (int q = 0; q < 6; ++q) o[2 + q] = id[q];
+        } else {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                const int sh = 8 * pl;
+                o[2 + 2 * pl] = ((id[0] >> sh) & 255u) | (((id[1] >> sh) & 255u) << 8) |
+                                (((id[2] >> sh) & 255u) << 16) | (((id[3] >> sh) & 255u) << 24);
+                o[3 + 2 * pl] = ((id[4] >> sh) & 255u) | (((id[5] >> sh) & 255u) << 8) |
+                                (((id[6] >> sh) & 255u) << 16) | (((id[7] >> sh) & 255u) << 24);
+            }
         }
         uint4* dst = reinterpret_cast<uint4*>(leaf + g * 8ull);
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -149,12 +158,13 @@ extern "C" size_t pb200_walk_bucket_workspace_bytes(int64_t num_nodes) {
     return wbkt_carve(nullptr, num_nodes > 0 ? num_nodes : 0).total;
 }
 
-extern "C" int pb200_walk_bucket_plan(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
-                                      uint32_t* meta, uint64_t* info_out, void* workspace,
-                                      size_t workspace_bytes, pb200_stream_t stream_) {
+extern "C" int pb200_walk_bucket_plan_ex(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
+                                         uint32_t* meta, uint64_t* info_out, void* workspace,
+                                         size_t workspace_bytes, int leaf_format, pb200_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PB_REQUIRE(num_nodes > 0 && num_nodes < 2147483647ll && row_ptr && cum && meta && info_out && workspace,
                "walk_bucket_plan: bad arguments");
+    PB_REQUIRE(leaf_format == PB200_LEAF_BUCKET || leaf_format == PB200_LEAF_BUCKET32, "walk_bucket_plan: unknown format");
     PB_REQUIRE((uintptr_t)meta % 16 == 0, "walk_bucket_plan: meta must be 16-byte aligned");
     WbktWs w = wbkt_carve(workspace, num_nodes);
     if (workspace_bytes < w.total) {
@@ -164,9 +174,14 @@ extern "C" int pb200_walk_bucket_plan(const int64_t* row_ptr, const void* cum, i
     PB_CUDA(cudaMemsetAsync(info_out, 0, 2 * sizeof(uint64_t), stream));
     PB_CUDA(cudaMemsetAsync(w.cnt + num_nodes, 0, sizeof(unsigned long long), stream));
     const unsigned blocks = (unsigned)(ceil_div(num_nodes, 8) < kSMs * 16 ? ceil_div(num_nodes, 8) : kSMs * 16);
-    wbkt_plan_kernel<<<blocks, 256, 0, stream>>>(row_ptr, static_cast<const uint32_t*>(cum), num_nodes,
-                                                 reinterpret_cast<uint4*>(meta), w.cnt,
-                                                 reinterpret_cast<unsigned long long*>(info_out));
+    if (leaf_format == PB200_LEAF_BUCKET32)
+        wbkt_plan_kernel<6><<<blocks, 256, 0, stream>>>(row_ptr, static_cast<const uint32_t*>(cum), num_nodes,
+                                                        reinterpret_cast<uint4*>(meta), w.cnt,
+                                                        reinterpret_cast<unsigned long long*>(info_out));
+    else
+        wbkt_plan_kernel<8><<<blocks, 256, 0, stream>>>(row_ptr, static_cast<const uint32_t*>(cum), num_nodes,
+                                                        reinterpret_cast<uint4*>(meta), w.cnt,
+                                                        reinterpret_cast<unsigned long long*>(info_out));
     int rc = check_launch("wbkt_plan_kernel");
     if (rc) return rc;
     size_t tb = w.temp_bytes;
@@ -176,20 +191,41 @@ extern "C" int pb200_walk_bucket_plan(const int64_t* row_ptr, const void* cum, i
     return check_launch("wbkt_total_kernel");
 }
 
-extern "C" int pb200_walk_bucket_fill(const int64_t* row_ptr, const int32_t* col, const void* cum,
-                                      int64_t num_nodes, const void* workspace, uint32_t* meta,
-                                      uint32_t* leaf, uint64_t total_buckets, pb200_stream_t stream) {
+extern "C" int pb200_walk_bucket_plan(const int64_t* row_ptr, const void* cum, int64_t num_nodes,
+                                      uint32_t* meta, uint64_t* info_out, void* workspace,
+                                      size_t workspace_bytes, pb200_stream_t stream) {
+    return pb200_walk_bucket_plan_ex(row_ptr, cum, num_nodes, meta, info_out, workspace, workspace_bytes,
+                                     PB200_LEAF_BUCKET, stream);
+}
+
+extern "C" int pb200_walk_bucket_fill_ex(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                                         int64_t num_nodes, const void* workspace, uint32_t* meta,
+                                         uint32_t* leaf, uint64_t total_buckets, int leaf_format, pb200_stream_t stream) {
     PB_REQUIRE(num_nodes > 0 && row_ptr && col && cum && workspace && meta && leaf,
                "walk_bucket_fill: bad arguments");
-    PB_REQUIRE(num_nodes <= (1 << 24), "walk_bucket_fill: the bucket format holds 24-bit node ids");
+    PB_REQUIRE(leaf_format == PB200_LEAF_BUCKET || leaf_format == PB200_LEAF_BUCKET32, "walk_bucket_fill: unknown format");
+    PB_REQUIRE(leaf_format == PB200_LEAF_BUCKET32 || num_nodes <= (1 << 24),
+               "walk_bucket_fill: PB200_LEAF_BUCKET holds 24-bit node ids (use PB200_LEAF_BUCKET32)");
     PB_REQUIRE(total_buckets < 4294967296ull, "walk_bucket_fill: more than 2^32 buckets");
     PB_REQUIRE((uintptr_t)leaf % 32 == 0 && (uintptr_t)meta % 16 == 0, "walk_bucket_fill: leaf/meta alignment");
     if (total_buckets == 0) return PB200_OK;
     WbktWs w = wbkt_carve(const_cast<void*>(workspace), num_nodes);
     const int64_t want = ceil_div((int64_t)total_buckets, 256);
     const unsigned blocks = (unsigned)(want < (int64_t)kSMs * 32 ? want : (int64_t)kSMs * 32);
-    wbkt_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        row_ptr, col, static_cast<const uint32_t*>(cum), num_nodes, w.cnt, reinterpret_cast<uint4*>(meta), leaf,
-        (unsigned long long)total_buckets);
+    if (leaf_format == PB200_LEAF_BUCKET32)
+        wbkt_fill_kernel<6><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            row_ptr, col, static_cast<const uint32_t*>(cum), num_nodes, w.cnt, reinterpret_cast<uint4*>(meta), leaf,
+            (unsigned long long)total_buckets);
+    else
+        wbkt_fill_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            row_ptr, col, static_cast<const uint32_t*>(cum), num_nodes, w.cnt, reinterpret_cast<uint4*>(meta), leaf,
+            (unsigned long long)total_buckets);
     return check_launch("wbkt_fill_kernel");
+}
+
+extern "C" int pb200_walk_bucket_fill(const int64_t* row_ptr, const int32_t* col, const void* cum,
+                                      int64_t num_nodes, const void* workspace, uint32_t* meta,
+                                      uint32_t* leaf, uint64_t total_buckets, pb200_stream_t stream) {
+    return pb200_walk_bucket_fill_ex(row_ptr, col, cum, num_nodes, workspace, meta, leaf, total_buckets,
+                                     PB200_LEAF_BUCKET, stream);
 }

@@ -229,7 +229,8 @@ __device__ __forceinline__ uint4 ld_meta(const uint4* p) {
     return r;
 }
 
-template <int kLd = 0>
+template <bool k32> __device__ __forceinline__ int bucket_pick(const U8& w, uint32_t tr);
+template <int kLd = 0, bool k32 = false>
 __device__ __forceinline__ int bucket_step(const uint4* __restrict__ meta,
                                            const uint32_t* __restrict__ leaf, int cur, uint32_t a,
                                            uint32_t b) {
@@ -244,12 +245,7 @@ __device__ __forceinline__ int bucket_step(const uint4* __restrict__ meta,
     const U8 w = ld256_bucket<kLd>(leaf + ((size_t)(m.x + j) << 3));
     // slots with rel <= tr, bytewise: 0x80 + tr - rel keeps bit 7 iff rel <= tr (rel <= 128, tr <= 127:
     // no borrow crosses a byte).  rel is ascending and the edge holding t is in the bucket: c <= 7.
-    const uint32_t t4 = tr * 0x01010101u + 0x80808080u;
-    const uint32_t c = (uint32_t)(__popc((t4 - w.v[0]) & 0x80808080u) + __popc((t4 - w.v[1]) & 0x80808080u));
-    const uint32_t r0 = __byte_perm(w.v[2], w.v[3], c);
-    const uint32_t r1 = __byte_perm(w.v[4], w.v[5], c);
-    const uint32_t r2 = __byte_perm(w.v[6], w.v[7], c);
-    return (int)(__byte_perm(__byte_perm(r0, r1, 0x0040u), r2, 0x0410u) & 0x00FFFFFFu);
+    return bucket_pick<k32>(w, tr);
 }
 
 // Predicated forms for the batched kernel: kB independent walks per lane are kept in flight, their
@@ -291,8 +287,16 @@ __device__ __forceinline__ uint32_t bucket_locate(const uint4& m, uint32_t a, ui
     tr = t - (j << m.w);
     return m.x + j;
 }
+// k32 = PB200_LEAF_BUCKET32: six slots, rel bytes 0..5 (bytes 6..7 hold 128 and are masked out), ids as words 2..7
+template <bool k32>
 __device__ __forceinline__ int bucket_pick(const U8& w, uint32_t tr) {
     const uint32_t t4 = tr * 0x01010101u + 0x80808080u;
+    if (k32) {
+        const uint32_t c = (uint32_t)(__popc((t4 - w.v[0]) & 0x80808080u) + __popc((t4 - w.v[1]) & 0x00008080u));
+        const bool odd = c & 1u;                                   // c <= 5: the edge holding t is in the bucket
+        const uint32_t lo = odd ? w.v[3] : w.v[2], mid = odd ? w.v[5] : w.v[4], hi = odd ? w.v[7] : w.v[6];
+        return (int)(c >= 4u ? hi : (c >= 2u ? mid : lo));
+    }
     const uint32_t c = (uint32_t)(__popc((t4 - w.v[0]) & 0x80808080u) + __popc((t4 - w.v[1]) & 0x80808080u));
     const uint32_t r0 = __byte_perm(w.v[2], w.v[3], c);
     const uint32_t r1 = __byte_perm(w.v[4], w.v[5], c);
@@ -300,7 +304,7 @@ __device__ __forceinline__ int bucket_pick(const U8& w, uint32_t tr) {
     return (int)(__byte_perm(__byte_perm(r0, r1, 0x0040u), r2, 0x0410u) & 0x00FFFFFFu);
 }
 
-enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3, kIndexedCompact = 4, kIndexedBucket = 5 };
+enum WalkMode { kFlatU32 = 0, kFlatF64 = 1, kCountTrace = 2, kIndexed = 3, kIndexedCompact = 4, kIndexedBucket = 5, kIndexedBucket32 = 6 };
 
 // 8 sorted values per lane (descending) -- Batcher odd-even merge sort network, 19 exchanges
 __device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {   // a >= b afterwards
@@ -417,9 +421,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_topt_kernel(const WalkPa
                     const uint64_t k53 = (l & 1) ? uniform53(r.v[2], r.v[3])
                                                  : uniform53(r.v[0], r.v[1]);
                     int next = -1;
-                    if (kMode == kIndexedBucket) {
-                        next = (l & 1) ? bucket_step(p.meta, p.leaf, cur, r.v[2], r.v[3])
-                                       : bucket_step(p.meta, p.leaf, cur, r.v[0], r.v[1]);
+                    if (kMode == kIndexedBucket || kMode == kIndexedBucket32) {
+                        next = (l & 1) ? bucket_step<0, kMode == kIndexedBucket32>(p.meta, p.leaf, cur, r.v[2], r.v[3])
+                                       : bucket_step<0, kMode == kIndexedBucket32>(p.meta, p.leaf, cur, r.v[0], r.v[1]);
                     } else if (kMode == kIndexed || kMode == kIndexedCompact) {
                         next = indexed_step<kBin, kMode == kIndexedCompact>(p.meta, p.idx, p.leaf, cur, k53);
                     } else {
@@ -753,19 +757,19 @@ __global__ void __launch_bounds__(256, kMinBlocks) walk_bucket_batched_kernel(co
                 }
                 uint4 m[kB];
 #pragma unroll
-                for (int i = 0; i < kB; ++i) m[i] = ld_meta_if<kLd>(p.meta + cur[i], alive[i]);
+                for (int i = 0; i < kB; ++i) m[i] = ld_meta_if<(kLd & 3)>(p.meta + cur[i], alive[i]);
                 U8 w[kB]; uint32_t tr[kB];
 #pragma unroll
                 for (int i = 0; i < kB; ++i) {
                     alive[i] = alive[i] && m[i].y != 0u;       // dead end: random_walk.py:68-69
                     const uint32_t blk = bucket_locate(m[i], (l & 1) ? r[i].v[2] : r[i].v[0], (l & 1) ? r[i].v[3] : r[i].v[1], tr[i]);
-                    w[i] = ld256_bucket_if<kLd>(p.leaf + ((size_t)blk << 3), alive[i]);
+                    w[i] = ld256_bucket_if<(kLd & 3)>(p.leaf + ((size_t)blk << 3), alive[i]);
                 }
                 int next[kB]; uint32_t fs[kB];
 #pragma unroll
                 for (int i = 0; i < kB; ++i) {
                     const int walk = base + 32 * i + lane;
-                    next[i] = alive[i] ? bucket_pick(w[i], tr[i]) : -1;
+                    next[i] = alive[i] ? bucket_pick<(kLd & 4) != 0>(w[i], tr[i]) : -1;   // kLd & 4: 32-bit ids
                     fs[i] = (uint32_t)(walk * L + l);
                     if (kTrace) { if (walk < p.W) p.trace_out[(s * p.W + walk) * L + l] = next[i]; }
                     cur[i] = alive[i] ? next[i] : cur[i];
@@ -828,7 +832,7 @@ static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
     const int batch = batch_env >= 0 ? batch_env : (small ? 4 : PB200_WALK_BATCH_DEFAULT);
     const int minb = minb_set ? minb_env : (batch == 4 ? 4 : 6);
     static const int ld = [] { const char* e = getenv("PB200_WALK_LD"); return e ? atoi(e) : 2; }();
-    if (batch > 0) {
+    if (batch > 0 || p.leaf_format == PB200_LEAF_BUCKET32) {      // 32-bit ids: the batched kernel only
         const int64_t cap = (int64_t)kSMs * 32;
         int64_t blocks = ceil_div(p.n, (int64_t)8);
         if (blocks > cap) blocks = cap;
@@ -838,11 +842,13 @@ static int launch_walk_bucket(const WalkParams& p, cudaStream_t stream) {
 #define PB_BB(L_, T_, LD_) do { if (batch == 2 && minb == 5) PB_BK(L_, T_, LD_, 2, 5); if (batch == 2) PB_BK(L_, T_, LD_, 2, 6); \
                                 if (batch == 4 && minb == 5) PB_BK(L_, T_, LD_, 4, 5); if (batch == 4 && minb == 3) PB_BK(L_, T_, LD_, 4, 3); \
                                 if (batch == 4) PB_BK(L_, T_, LD_, 4, 4); PB_BK(L_, T_, LD_, 1, 6); } while (0)
-#define PB_BL(L_, T_) do { if (ld == 0) PB_BB(L_, T_, 0); PB_BB(L_, T_, 2); } while (0)
+#define PB_BB32(L_, T_) do { if (batch == 2) PB_BK(L_, T_, 6, 2, 6); if (batch == 4) PB_BK(L_, T_, 6, 4, 4); PB_BK(L_, T_, 6, 1, 6); } while (0)
+#define PB_BL(L_, T_) do { if (p.leaf_format == PB200_LEAF_BUCKET32) PB_BB32(L_, T_); if (ld == 0) PB_BB(L_, T_, 0); PB_BB(L_, T_, 2); } while (0)
         if (p.trace_out) { if (p.L == 2) PB_BL(2, true); PB_BL(0, true); }
         if (p.L == 2) PB_BL(2, false);
         PB_BL(0, false);
 #undef PB_BL
+#undef PB_BB32
 #undef PB_BB
 #undef PB_BK
     }
@@ -911,9 +917,11 @@ static int launch_walk(WalkParams& p, int cum_kind, bool count_only, cudaStream_
     if (!p.meta)
         return cum_kind == 0 ? launch_variant<kFlatU32, false, true, 1>(p, warps, smem, stream)
                              : launch_variant<kFlatF64, false, true, 1>(p, warps, smem, stream);
-    if (p.leaf_format == PB200_LEAF_BUCKET) {
+    if (p.leaf_format == PB200_LEAF_BUCKET || p.leaf_format == PB200_LEAF_BUCKET32) {
         if (bucket_fast_ok(p) && !(v & 1)) return launch_walk_bucket(p, stream);
-        return launch_variant<kIndexedBucket, false, true, 1>(p, warps, smem, stream);   // generic sizes
+        return p.leaf_format == PB200_LEAF_BUCKET32
+                   ? launch_variant<kIndexedBucket32, false, true, 1>(p, warps, smem, stream)
+                   : launch_variant<kIndexedBucket, false, true, 1>(p, warps, smem, stream);   // generic sizes
     }
     const bool bin = v & 2, reg = v & 4;
     const int minb = v >> 4;
@@ -987,7 +995,8 @@ extern "C" int pb200_walk_topt_indexed_ex(const uint32_t* meta, const uint32_t* 
     PB_REQUIRE(meta && leaf && starts && out_ids && out_counts && out_weights && out_nvalid,
                "walk_topt_indexed: null pointer");
     WalkParams p{};
-    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || leaf_format == PB200_LEAF_COMPACT || leaf_format == PB200_LEAF_BUCKET,
+    PB_REQUIRE(leaf_format == PB200_LEAF_WIDE || leaf_format == PB200_LEAF_COMPACT || leaf_format == PB200_LEAF_BUCKET ||
+                   leaf_format == PB200_LEAF_BUCKET32,
                "walk_topt_indexed: unknown leaf format %d", leaf_format);
     p.leaf_format = leaf_format;
     p.meta = reinterpret_cast<const uint4*>(meta); p.idx = idx; p.leaf = leaf; p.starts = starts;
@@ -1010,7 +1019,7 @@ extern "C" int pb200_walk_topt_indexed_multi(const uint32_t* meta, const uint32_
     WalkParams probe{};
     probe.W = num_walks; probe.L = walk_length; probe.T = num_neighbors;
     static const bool forced_generic = [] { const char* e = getenv("PB200_WALK_VARIANT"); return e && (atoi(e) & 1); }();
-    if (num_epochs > 1 && n > 0 && leaf_format == PB200_LEAF_BUCKET && num_walks > 0 && walk_length > 0 &&
+    if (num_epochs > 1 && n > 0 && (leaf_format == PB200_LEAF_BUCKET || leaf_format == PB200_LEAF_BUCKET32) && num_walks > 0 && walk_length > 0 &&
         num_neighbors > 0 && bucket_fast_ok(probe) && !forced_generic) {
         PB_REQUIRE(meta && leaf && starts && out_ids && out_counts && out_weights && out_nvalid,
                    "walk_topt_indexed_multi: null pointer");

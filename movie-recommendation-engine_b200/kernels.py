@@ -51,47 +51,55 @@ def _aligned_empty(n_int32, align, dev):
     return t
 
 
-def _build_bucket_index(csr):
+def _build_bucket_index(csr, wide_ids=None):
     """Direct-addressed bucket index (pb200_walk_bucket_*): meta -> one 32-byte bucket per walk step.
-    Returns False (csr untouched) when the format does not apply: a zero-weight edge, more than
-    2^24 nodes, or weights so heavy that the buckets would take more than ~48 bytes per edge."""
+    wide_ids: None = 8 slots with 24-bit ids when the graph has at most 2^24 nodes, else 6 slots with
+    32-bit ids (PB200_LEAF_BUCKET32); True forces the 32-bit form.  Returns False (csr untouched) when the
+    format does not apply: a zero-weight edge, or weights so heavy that the buckets would take more
+    than ~48 (64 for the 6-slot form) bytes per edge."""
     dev = csr.device
     st = stream_ptr(dev)
     Nn, E = csr.num_nodes, csr.num_edges
-    if Nn > (1 << 24) or E == 0:
+    if E == 0:
         return False
+    if wide_ids is None:
+        wide_ids = Nn > (1 << 24)
+    if not wide_ids and Nn > (1 << 24):
+        return False
+    fmt = N.LEAF_BUCKET32 if wide_ids else N.LEAF_BUCKET
     ws_bytes = lib().pb200_walk_bucket_workspace_bytes(Nn)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     meta = _aligned_empty(4 * Nn, 16, dev)
     info = torch.zeros(2, dtype=torch.int64, device=dev)
-    check(lib().pb200_walk_bucket_plan(ptr(csr.row_ptr), ptr(csr.cum), Nn, ptr(meta), ptr(info), ptr(ws),
-                                       ws_bytes, st), "walk_bucket_plan")
+    check(lib().pb200_walk_bucket_plan_ex(ptr(csr.row_ptr), ptr(csr.cum), Nn, ptr(meta), ptr(info), ptr(ws),
+                                          ws_bytes, fmt, st), "walk_bucket_plan")
     buckets, zero_edges = info.tolist()               # build-time sync
-    if zero_edges or buckets >= (1 << 32) or buckets * 32 > 48 * E + 64 * Nn:
+    if zero_edges or buckets >= (1 << 32) or buckets * 32 > (64 if wide_ids else 48) * E + 64 * Nn:
         return False
     leaf = _aligned_empty(8 * max(buckets, 1), 32, dev)
-    check(lib().pb200_walk_bucket_fill(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cum), Nn, ptr(ws), ptr(meta),
-                                       ptr(leaf), buckets, st), "walk_bucket_fill")
+    check(lib().pb200_walk_bucket_fill_ex(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cum), Nn, ptr(ws), ptr(meta),
+                                          ptr(leaf), buckets, fmt, st), "walk_bucket_fill")
     csr.meta = meta.view(Nn, 4)
     csr.idx = None
     csr.leaf = leaf.view(-1, 8)[:buckets]
-    csr.leaf_format = N.LEAF_BUCKET
+    csr.leaf_format = fmt
     return True
 
 
 def build_walk_index(csr, leaf=None):
     """Adds a sampling index to a uint32-quanta CSR.  `leaf` (or PB200_WALK_LEAF): "auto" (bucket index
-    when it applies, else the 8-ary tree with compact or wide leaves), "bucket", "compact", "wide"."""
+    when it applies -- 24-bit ids up to 2^24 nodes, 32-bit ids beyond -- else the 8-ary tree with compact or
+    wide leaves), "bucket", "bucket32" (the 32-bit-id bucket form on any graph), "compact", "wide"."""
     if csr.cum_kind != 0 or csr.num_nodes == 0 or csr.num_edges == 0:     # nothing to index: the flat kernel serves
         return csr
     import os
     want = (leaf or os.environ.get("PB200_WALK_LEAF", "auto")).lower()
-    if want in ("auto", "bucket"):
-        if _build_bucket_index(csr):
+    if want in ("auto", "bucket", "bucket32"):
+        if _build_bucket_index(csr, wide_ids=True if want == "bucket32" else None):
             return csr
-        if want == "bucket":
-            raise N.NativeError("the bucket sampling index does not apply to this graph (zero-weight edges, "
-                                "more than 2^24 nodes, or very heavy weights)")
+        if want != "auto":
+            raise N.NativeError("the bucket sampling index does not apply to this graph (zero-weight edges "
+                                "or very heavy weights)")
     dev = csr.device
     st = stream_ptr(dev)
     Nn = csr.num_nodes

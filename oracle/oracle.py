@@ -127,12 +127,14 @@ def _pick(cum, r0, r1, k53):
     return r0 + min(i, r1 - r0 - 1)
 
 
-def walk_bucket_index(row_ptr, col, cum):
+def walk_bucket_index(row_ptr, col, cum, slots=8):
     """numpy restatement of the direct-addressed sampling index the walk kernel reads
-    (csrc/walk_bucket.cu, PB200_LEAF_BUCKET): per row a shift s and ceil(S / 2^s) 32-byte buckets
-    {8 x u8 min(cum - j 2^s, 2^s) (unused: 128), 8 x id byte 0, 8 x id byte 1, 8 x id byte 2}.
+    (csrc/walk_bucket.cu): per row a shift s and ceil(S / 2^s) 32-byte buckets.
+    slots=8 (PB200_LEAF_BUCKET): {8 x u8 min(cum - j 2^s, 2^s) (unused: 128), 8 x id byte 0, 8 x id byte 1,
+    8 x id byte 2}; slots=6 (PB200_LEAF_BUCKET32): {6 x u8 rel, 2 x 128, 6 x little-endian u32 id}.
     Returns (meta uint32 [N, 4] = {first bucket, degree, S, s}, leaf uint8 [buckets, 32]) or None
     when a zero-weight edge makes the format unusable.  Pure loops: small graphs only."""
+    assert slots in (6, 8)
     N = len(row_ptr) - 1
     meta = np.zeros((N, 4), np.uint32)
     blocks = []
@@ -145,8 +147,8 @@ def walk_bucket_index(row_ptr, col, cum):
         if deg and np.any(c == prev):
             return None
         s = 7
-        for i in range(deg - 8):                       # edges i..i+8 must not share a bucket
-            x = int(c[i] - 1) ^ int(c[i + 7])
+        for i in range(deg - slots):                   # edges i..i+slots must not share a bucket
+            x = int(c[i] - 1) ^ int(c[i + slots - 1])
             s = min(s, x.bit_length() - 1)
         meta[v] = (len(blocks), deg, S, s)
         w = 1 << s
@@ -157,17 +159,20 @@ def walk_bucket_index(row_ptr, col, cum):
             q = 0
             e = first
             while e < deg and (e == first or prev[e] < lo + w):
-                assert q < 8, "bucket overflow: the shift rule is wrong"
+                assert q < slots, "bucket overflow: the shift rule is wrong"
                 blk[q] = min(int(c[e]) - lo, w)
                 nid = int(col[a + e])
-                blk[8 + q], blk[16 + q], blk[24 + q] = nid & 255, (nid >> 8) & 255, (nid >> 16) & 255
+                if slots == 8:
+                    blk[8 + q], blk[16 + q], blk[24 + q] = nid & 255, (nid >> 8) & 255, (nid >> 16) & 255
+                else:
+                    blk[8 + 4 * q: 12 + 4 * q] = [(nid >> (8 * k)) & 255 for k in range(4)]
                 q += 1; e += 1
             blocks.append(blk)
     leaf = np.stack(blocks) if blocks else np.zeros((0, 32), np.uint8)
     return meta, leaf
 
 
-def walk_bucket_pick(meta, leaf, v, k53):
+def walk_bucket_pick(meta, leaf, v, k53, slots=8):
     """The bucket walk step: neighbour chosen at node v for the 53-bit uniform numerator k53, or -1."""
     first, deg, S, s = (int(x) for x in meta[v])
     if deg == 0:
@@ -175,8 +180,10 @@ def walk_bucket_pick(meta, leaf, v, k53):
     t = (k53 * S) >> 53
     blk = leaf[first + (t >> s)]
     tr = t & ((1 << s) - 1)
-    c = int(np.sum(blk[:8] <= tr))
-    assert c < 8
+    c = int(np.sum(blk[:slots] <= tr))
+    assert c < slots
+    if slots == 6:
+        return int.from_bytes(bytes(blk[8 + 4 * c: 12 + 4 * c]), "little")
     return int(blk[8 + c]) | (int(blk[16 + c]) << 8) | (int(blk[24 + c]) << 16)
 
 

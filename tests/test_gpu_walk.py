@@ -256,6 +256,54 @@ def test_bucket_index_structure_and_walks(K, wmax):
             np.testing.assert_array_equal(_np(a), _np(b))
 
 
+@pytest.mark.parametrize("wmax", [1, 10, 120])
+def test_bucket32_index_structure_and_walks(K, wmax):
+    """PB200_LEAF_BUCKET32 (six slots, 32-bit ids -- what graphs with more than 2^24 nodes get): the index
+    equals the numpy restatement, and walks through it equal the flat search and the C oracle, with
+    neighbour ids above 2^24 (the 24-bit forms would truncate them)."""
+    from mre_b200 import _native as NV
+    rng = np.random.Generator(np.random.PCG64(60 + wmax))
+    degs = [0, 1, 5, 6, 7, 8, 9, 63, 64, 65, 511, 512, 513, 4097, 5000]
+    ei, w = _deep_graph(rng, degs, wmax)
+    N = (1 << 24) + 6000
+    ei = ei.copy()
+    ei[1] += np.where(ei[1] % 3 == 0, 1 << 24, 0)                  # a third of the destinations beyond 24 bits
+    back = np.stack([ei[1][:4000], ei[0][:4000]])                  # some edges back so that step 2 continues
+    ei2 = np.concatenate([ei, back], axis=1); w2 = np.concatenate([w, w[:4000]])
+    csr = K.csr_build(torch.from_numpy(ei2), torch.from_numpy(w2), num_nodes=N)
+    assert csr.leaf_format == NV.LEAF_BUCKET32 and csr.idx is None      # auto: > 2^24 nodes
+    row_ptr, col, cum = O.csr_build(ei2, w2, N, 1)
+    assert col.max() >= (1 << 24)
+    # structure on the rows that have edges (the restatement loops over rows in Python: compare on a compacted copy)
+    rows = np.flatnonzero(np.diff(row_ptr))[:200]
+    sub_ptr = np.zeros(len(rows) + 1, np.int64); sub_ptr[1:] = np.cumsum(np.diff(row_ptr)[rows])
+    sel = np.concatenate([np.arange(row_ptr[v], row_ptr[v + 1]) for v in rows])
+    meta, leaf = O.walk_bucket_index(sub_ptr, col[sel], cum[sel], slots=6)
+    got_meta = _np(csr.meta).view(np.uint32)[rows]
+    np.testing.assert_array_equal(got_meta[:, 1:], meta[:, 1:])
+    got_leaf = np.ascontiguousarray(_np(csr.leaf)).view(np.uint8).reshape(-1, 32)
+    for i in range(len(rows)):
+        nb = int(((meta[i, 2] - 1) >> meta[i, 3]) + 1)
+        np.testing.assert_array_equal(got_leaf[got_meta[i, 0]:got_meta[i, 0] + nb], leaf[meta[i, 0]:meta[i, 0] + nb])
+    starts = np.concatenate([np.arange(len(degs)), np.unique(ei2[0][ei2[0] >= (1 << 24)])[:50]])
+    for (W, L, T) in [(100, 2, 10), (64, 3, 8), (200, 3, 20), (33, 1, 32), (7, 5, 3)]:
+        got = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 77, 3, return_trace=True)
+        flat = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 77, 3, return_trace=True, use_index=False)
+        o = O.c_walk_topt(row_ptr, col, cum, starts, W, L, T, 77, 3, return_trace=True)
+        for a, b, key in zip(got, flat, ["ids", "counts", "w32", "nvalid", "trace"]):
+            np.testing.assert_array_equal(_np(a), _np(b))
+            np.testing.assert_array_equal(_np(a), o[key])
+        assert _np(got[4]).max() >= (1 << 24)
+        notrace = K.walk_topt(csr, torch.from_numpy(starts), W, L, T, 77, 3)
+        for a, b in zip(notrace, got[:4]):
+            np.testing.assert_array_equal(_np(a), _np(b))
+    multi = K.walk_topt(csr, torch.from_numpy(starts), 100, 2, 10, 77, 3, num_epochs=2)
+    for e in range(2):
+        one = K.walk_topt(csr, torch.from_numpy(starts), 100, 2, 10, 77, 3 + e)
+        for a, b in zip(multi, one):
+            np.testing.assert_array_equal(_np(a[e]), _np(b))
+
+
 def test_bucket_index_fallbacks(K):
     """Graphs the bucket format does not cover keep the tree index: a zero-weight edge, weights so
     heavy that buckets would dwarf the edge list.  An explicit request raises."""

@@ -28,24 +28,24 @@ def small_graphs(draw, max_nodes=40, max_edges=400, weights=True):
 
 
 @settings(max_examples=60, **SET)
-@given(small_graphs())
-def test_bucket_index_equals_flat_rule_on_arbitrary_rows(g):
+@given(small_graphs(), st.sampled_from([8, 6]))
+def test_bucket_index_equals_flat_rule_on_arbitrary_rows(g, slots):
     n, ei, w = g
     row_ptr, col, cum = O.csr_build(ei, w, n, 1)
-    built = O.walk_bucket_index(row_ptr, col, cum)
+    built = O.walk_bucket_index(row_ptr, col, cum, slots)
     assert built is not None
     meta, leaf = built
     rng = np.random.Generator(np.random.PCG64(int(ei.sum()) % 1000))
     for v in range(n):
         a, b = int(row_ptr[v]), int(row_ptr[v + 1])
         if a == b:
-            assert O.walk_bucket_pick(meta, leaf, v, 5) == -1
+            assert O.walk_bucket_pick(meta, leaf, v, 5, slots) == -1
             continue
         S = int(cum[b - 1])
         for t in set([0, S - 1] + rng.integers(0, S, 8).tolist()):
             k53 = -((-t << 53) // S)
             want = int(col[a + np.searchsorted(cum[a:b], np.uint32(t), side="right")])
-            assert O.walk_bucket_pick(meta, leaf, v, k53) == want
+            assert O.walk_bucket_pick(meta, leaf, v, k53, slots) == want
 
 
 @settings(max_examples=25, **SET)
@@ -70,7 +70,7 @@ def test_numpy_oracle_equals_c_oracle(g, W, L, T, seed):
 @pytest.mark.gpu
 @settings(max_examples=30, **SET)
 @given(small_graphs(max_nodes=60, max_edges=900), st.sampled_from([(100, 2, 10), (7, 5, 3), (33, 2, 32), (64, 3, 50), (1, 1, 1)]),
-       st.integers(0, 2**40), st.sampled_from(["bucket", "compact", "wide"]))
+       st.integers(0, 2**40), st.sampled_from(["bucket", "bucket32", "compact", "wide"]))
 def test_walk_kernels_equal_the_oracle_on_generated_graphs(g, shape, seed, leaf):
     import mre_b200  # noqa: F401
     from mre_b200 import kernels as K

@@ -18,12 +18,17 @@ def _graph(rng, degs, wmax, n_dst=4000):
     return O.csr_build(ei, w[perm], max(len(degs), n_dst), 1)
 
 
+@pytest.mark.parametrize("slots", [8, 6])
 @pytest.mark.parametrize("wmax", [1, 10, 60, 300])
-def test_bucket_index_picks_the_flat_rule_edge_for_every_t(wmax):
+def test_bucket_index_picks_the_flat_rule_edge_for_every_t(wmax, slots):
+    """slots = 8: PB200_LEAF_BUCKET (24-bit ids); slots = 6: PB200_LEAF_BUCKET32 (32-bit ids, ids up to 2^31)."""
     rng = np.random.Generator(np.random.PCG64(wmax))
-    degs = [0, 1, 2, 7, 8, 9, 10, 17, 64, 65, 300, 1000]
+    degs = [0, 1, 2, 5, 6, 7, 8, 9, 10, 17, 64, 65, 300, 1000]
     row_ptr, col, cum = _graph(rng, degs, wmax)
-    built = O.walk_bucket_index(row_ptr, col, cum)
+    if slots == 6:
+        col = (col.astype(np.int64) * 500000 + 7).astype(np.int32)      # ids up to 2e9: beyond 24 bits
+        assert col.max() > (1 << 30)
+    built = O.walk_bucket_index(row_ptr, col, cum, slots)
     assert built is not None
     meta, leaf = built
     assert meta[:, 3].max() <= 7 and leaf[:, :8].max() <= 128
@@ -32,7 +37,7 @@ def test_bucket_index_picks_the_flat_rule_edge_for_every_t(wmax):
         S = int(cum[a + d - 1]) if d else 0
         assert meta[v, 1] == d and meta[v, 2] == S
         if d == 0:
-            assert O.walk_bucket_pick(meta, leaf, v, 123) == -1
+            assert O.walk_bucket_pick(meta, leaf, v, 123, slots) == -1
             continue
         # every t in [0, S): drive the pick with a k53 that lands exactly on t
         ts = np.arange(S) if S <= 6000 else np.unique(np.concatenate(
@@ -41,7 +46,7 @@ def test_bucket_index_picks_the_flat_rule_edge_for_every_t(wmax):
         for t, wnt in zip(ts.tolist(), want.tolist()):
             k53 = -((-t << 53) // S)                      # smallest k with floor(k S / 2^53) == t
             assert (k53 * S) >> 53 == t and k53 < (1 << 53)
-            assert O.walk_bucket_pick(meta, leaf, v, k53) == wnt
+            assert O.walk_bucket_pick(meta, leaf, v, k53, slots) == wnt
 
 
 def test_bucket_index_refuses_zero_weight_edges():
@@ -78,6 +83,27 @@ def test_device_step_bit_tricks_match_the_format():
         r = [_byte_perm(planes[p][0], planes[p][1], c) for p in range(3)]
         got = _byte_perm(_byte_perm(r[0], r[1], 0x0040), r[2], 0x0410) & 0xFFFFFF
         assert got == int(ids[c])
+
+
+def test_device_step_bit_tricks_six_slot_form():
+    """bucket_pick<true>: the count masks bytes 6..7 of the second word (they hold 128), the id is word 2 + c."""
+    rng = np.random.Generator(np.random.PCG64(15))
+    for _ in range(2000):
+        n = int(rng.integers(1, 7))
+        rel = np.sort(rng.integers(1, 129, n))
+        rel = np.concatenate([rel, np.full(8 - n, 128)]).astype(np.int64)
+        tr = int(rng.integers(0, 128))
+        w0 = sum(int(rel[i]) << (8 * i) for i in range(4))
+        w1 = sum(int(rel[4 + i]) << (8 * i) for i in range(4))
+        t4 = (tr * 0x01010101 + 0x80808080) & 0xFFFFFFFF
+        c = bin(((t4 - w0) & 0xFFFFFFFF) & 0x80808080).count("1") + bin(((t4 - w1) & 0xFFFFFFFF) & 0x00008080).count("1")
+        assert c == int(np.sum(rel[:6] <= tr))
+        if c > 5:
+            continue
+        ids = rng.integers(0, 1 << 31, 6).tolist()
+        odd = c & 1
+        lo, mid, hi = (ids[1] if odd else ids[0]), (ids[3] if odd else ids[2]), (ids[5] if odd else ids[4])
+        assert (hi if c >= 4 else (mid if c >= 2 else lo)) == ids[c]
 
 
 def test_split_product_equals_floor_k53_total_over_2_53():
