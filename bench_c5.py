@@ -5,9 +5,10 @@ bench.py (`run_c5`, every rank calls it) and a stand-alone CLI (`torchrun ... be
 
 C5 proper is 10 M items / 50 M users / 2 G ratings.  What runs here is C5 x `scale` (default 1/16: 625 k items,
 3.125 M users, 125 M ratings = 250 M directed edges, mean degrees unchanged), generated ON THE DEVICE
-(synthetic.bipartite_graph_device, Philox), replicated per rank.  scale = 1 is NOT run: the graph has 60 M
-nodes (the bucket sampling index holds 24-bit ids), and pb200_csr_build's radix-sort workspace for 4 G
-directed edges plus the int64 edge list exceed 180 GB -- see DESIGN.md section 6.
+(synthetic.bipartite_graph_device, Philox), replicated per rank.  The largest scale that was run is 1/2 (5 M items,
+30 M nodes, 2 G directed edges; the sampling index switches to 32-bit ids beyond 2^24 nodes).  scale = 1 is NOT
+run: the int64 edge list (64 GB) + weights + pb200_csr_build's sort workspace for 4 G directed edges exceed
+180 GB on one GPU -- it needs the graph itself sharded, see DESIGN.md section 6.
 Steps, each timed by CUDA events (max over ranks):
   graph generation, CSR + sampling index build (one-off)
   embeddings: 3 x sampling (one launch) + input projection + 3 conv layers + output projection, rows dealt

@@ -19,13 +19,16 @@
 //   (utils/random_walk.py:72-79).  The edge containing t overlaps the bucket containing t, so
 //   it is always present.
 //
-//   PB200_LEAF_BUCKET32 (graphs with more than 2^24 nodes): the same with SIX slots per block --
-//       bytes 0..5 rel_i, bytes 6..7 unused (128), bytes 8..31 six 32-bit neighbour ids.
 //   s = the largest shift (<= 7) for which no bucket is overlapped by 9 edges: edges i..i+8
 //   share a bucket iff (cum_i - 1) >> s == cum_{i+7} >> s, so
 //   s = min(7, min_i msb((cum_i - 1) xor cum_{i+7})).  Needs every weight >= 1 quantum and node
-//   ids < 2^24; otherwise the caller keeps the tree index.  Size: ~S/2^s blocks per row (rating
-//   graphs: s = 4, ~11 B per edge) -- the price of one sector per step.
+//   ids < 2^24.  Size: ~S/2^s blocks per row (rating graphs: s = 4, ~11 B per edge) -- the price of
+//   one sector per step.
+//
+//   PB200_LEAF_BUCKET32 (graphs with more than 2^24 nodes): the same with SIX slots per block --
+//       bytes 0..5 rel_i, bytes 6..7 unused (128), bytes 8..31 six 32-bit neighbour ids;
+//   the shift rule forbids 7 edges per bucket (xor with cum_{i+5}); ~16 B per edge on rating graphs.
+//   Zero-weight edges or very heavy weights: the caller keeps the tree index.
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
