@@ -20,6 +20,8 @@ Works with the NCCL backend on GPUs and with gloo on CPU tensors (host-logic tes
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -277,6 +279,23 @@ def _use_peer_exchange(model, dev, ws):
     return dist.get_backend() == "nccl" and model.precision != N.PREC_FP32 and not model.fuse_pool
 
 
+_WALK_STREAMS = {}
+
+
+def _fork_walks(rows):
+    env = os.environ.get("PB200_FORK_WALKS")
+    if env is not None:
+        return env != "0"
+    return rows <= 74 * 128
+
+
+def _walk_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _WALK_STREAMS:
+        _WALK_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _WALK_STREAMS[key]
+
+
 def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10, group=None,
                            epoch_base=None, epoch_dev=None, check_barriers=True, before_forward=None,
                            layout=None):
@@ -313,13 +332,27 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     # the walks -- by the time a rank reaches the first barrier every peer's h^(0) has long been written, so
     # the walk kernel absorbs the skew between ranks instead of the barrier.  Host features being uploaded
     # on a forked stream: walks first, so the upload runs under them.
+    # Peer exchange, small shards: the walks run on a FORKED stream beside the input projection and the first
+    # barrier -- a 61-tile GEMM (C2 on 8 GPUs) leaves most SMs idle and the barrier is a wait: 172.7 vs 183.5 us
+    # per step at 7,803 rows per rank (profiles/r2_sharded_per_op_2gpus_7803rows_forked_walks.json).  A shard
+    # whose GEMM fills the GPU loses from sharing it (31,212 rows per rank: 0.400 vs 0.367 ms), so the fork is
+    # taken only below half an SM-count of 128-row tiles.  PB200_FORK_WALKS=0 / 1 forces it off / on.
     batches = None
+    forked = None
     if before_forward is not None:
         batches = sample()
         before_forward()
+    elif pb is not None and dev.type == "cuda" and _fork_walks(rows):
+        main = torch.cuda.current_stream(dev)
+        forked = _walk_stream(dev)
+        fork_point = main.record_event()
     xd = N.dev_tensor(x_local, torch.float32, dev)
     h_loc = K.gather_dense(xd, *P(model.input_proj), flags=N.EPI_RELU | RND, precision=model.precision,
                            out=pb.local(0)[:rows] if pb is not None else None)
+    if forked is not None:                                      # queued after the GEMM so that its CTAs are placed first
+        forked.wait_event(fork_point)
+        with torch.cuda.stream(forked):
+            batches = sample()
     if batches is None:
         batches = sample()
     if pb is not None:
@@ -327,6 +360,13 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
         # written by its GEMM straight into this rank's peer-visible shard of the next layer's input.
         for i in range(model.num_layers):
             pb.barrier()                                        # every rank's h^(i) is in place
+            if forked is not None and i == 0:                   # join: the lists are needed from here on
+                main.wait_stream(forked)
+                if not torch.cuda.is_current_stream_capturing():   # (a capture's private pool is not shared)
+                    for b in batches:
+                        for t in b.as_args():
+                            if t is not None:
+                                t.record_stream(main)           # allocated on the forked stream, read on this one
             wf, bf = model._folded_layer(i)
             ids, wts, ll, wl = batches[i].as_args()
             h_neigh = K.pool_sharded(pb.ptr_array(i), ws, srows, num_items, h_loc.size(1), ids, wts, ll, wl,

@@ -23,11 +23,16 @@ for prec in (N.PREC_FP32, N.PREC_AUTO):
     full = model.get_embeddings(x.to(dev), sampler, 10)                 # every rank: unsharded
     sampler.epoch = 0
     lo, hi = SH.shard_range(M, rank, ws)
-    for layout in ("cyclic", "blocks"):
+    for layout, fork in (("cyclic", None), ("blocks", None), ("cyclic", "0"), ("cyclic", "1")):
+        # fork: walks on a second stream beside the input projection (default: small shards only) / serialised
+        os.environ.pop("PB200_FORK_WALKS", None)
+        if fork is not None:
+            os.environ["PB200_FORK_WALKS"] = fork
         sampler.epoch = 0
         rows = SH.local_slice(M, rank, ws, layout)
         mine = SH.get_embeddings_sharded(model, x[rows], sampler, M, 10, layout=layout)
-        assert torch.equal(mine, full[rows]), f"rank {rank}: sharded embeddings differ (precision {prec}, {layout})"
+        os.environ.pop("PB200_FORK_WALKS", None)
+        assert torch.equal(mine, full[rows]), f"rank {rank}: sharded embeddings differ (precision {prec}, {layout}, fork {fork})"
         back = SH.all_gather_rows(mine, M, layout=layout)
         assert torch.equal(back, full), f"rank {rank}: all_gather_rows({layout}) does not reassemble the matrix"
 rows = SH.local_slice(M, rank, ws)
