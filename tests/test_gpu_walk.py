@@ -414,3 +414,39 @@ print("RECIPE_A_OK")
 ''' % root
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0 and "RECIPE_A_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_integration_recipe_b_ctypes_stub_from_the_document():
+    """INTEGRATION.md recipe B: the ctypes stub is cut out of the document and executed as written (library path
+    relative to the repository root); the two methods it gives the reference's RandomWalkSampler reproduce the C
+    oracle's lists and float64 weights."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    sec = text[text.index("## B."):]
+    code = sec[sec.index("```python") + len("```python"):]
+    code = code[:code.index("```")]
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        exec(compile(code, "INTEGRATION.md#B", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    import mre_b200.synthetic as S
+    ei, w = S.bipartite_graph(300, 700, 9000, seed=8)
+    cls = ns["RandomWalkSampler"]
+    smp = cls.__new__(cls)                                  # the reference's __init__ (utils/random_walk.py:11-31) sets these
+    smp.edge_index, smp.edge_weights = torch.from_numpy(ei), torch.from_numpy(w)
+    smp.num_walks, smp.walk_length, smp.seed, smp.epoch = 100, 2, 77, 3
+    smp._prepare_adjacency_list()
+    starts = list(range(0, 300, 5))
+    nbrs, wts = smp.batch_sample_neighbors(starts, 10)
+    assert smp.epoch == 4
+    N = int(ei.max()) + 1
+    row_ptr, col, cum = O.csr_build(ei, w, N, 1)
+    o = O.c_walk_topt(row_ptr, col, cum, np.array(starts), 100, 2, 10, 77, 3)
+    for i in range(len(starts)):
+        k = int(o["nvalid"][i])
+        assert nbrs[i] == o["ids"][i, :k].tolist()
+        assert wts[i] == o["w64"][i, :k].tolist()
