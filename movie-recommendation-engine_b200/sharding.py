@@ -335,7 +335,7 @@ def get_embeddings_sharded(model, x_local, sampler, num_items, num_neighbors=10,
     # Peer exchange, small shards: the walks run on a FORKED stream beside the input projection and the first
     # barrier -- a 61-tile GEMM (C2 on 8 GPUs) leaves most SMs idle and the barrier is a wait: 172.7 vs 183.5 us
     # per step at 7,803 rows per rank (profiles/r2_sharded_per_op_2gpus_7803rows_forked_walks.json).  A shard
-    # whose GEMM fills the GPU loses from sharing it (31,212 rows per rank: 0.400 vs 0.367 ms), so the fork is
+    # whose GEMM fills the GPU loses from sharing it (15,606 rows per rank: 254 vs 244 us; 31,212: 0.400 vs 0.367 ms), so the fork is
     # taken only below half an SM-count of 128-row tiles.  PB200_FORK_WALKS=0 / 1 forces it off / on.
     batches = None
     forked = None
